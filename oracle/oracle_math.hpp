@@ -1,0 +1,124 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle for the unconfined_b200 parity tests.
+//
+// PARITY UNPINNED: the reference (klkuhlm/unconfined) ships no golden outputs and
+// no Fortran compiler exists in this environment, so this restatement cannot be
+// checked against the reference binary.  It is pinned only at component level
+// (J0 zeros vs mishra-neuman/malama-sp/besJ0zeros.dat, K0/K1 vs scipy's Amos,
+// quadrature/inversion identities) -- see tests/ and DESIGN.md.
+//
+// Nothing under unconfined_b200/ may include, link or call this file.  Only
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// legs use it, and only as the checker / CPU baseline.
+//
+// This header: complex arithmetic under GCC's Fortran rules (-fcx-fortran-rules:
+// 4-multiply product, Smith division without NaN/Inf rescue, real operands promoted
+// to complex before * and /), and thin wrappers over the glibc routines gfortran
+// lowers its intrinsics to (csqrt/ccosh/csinh/cexp/clog/cabs, j0/j1, lgamma).
+#pragma once
+#include <cmath>
+#include <limits>
+
+// glibc's C99 complex routines (in C++ <complex.h> maps to <complex>, so declare them)
+extern "C" {
+double _Complex csqrt(double _Complex) noexcept;
+double _Complex ccosh(double _Complex) noexcept;
+double _Complex csinh(double _Complex) noexcept;
+double _Complex cexp(double _Complex) noexcept;
+double _Complex clog(double _Complex) noexcept;
+double cabs(double _Complex) noexcept;
+long double _Complex csqrtl(long double _Complex) noexcept;
+long double _Complex ccoshl(long double _Complex) noexcept;
+long double _Complex csinhl(long double _Complex) noexcept;
+long double _Complex cexpl(long double _Complex) noexcept;
+long double _Complex clogl(long double _Complex) noexcept;
+long double cabsl(long double _Complex) noexcept;
+}
+
+namespace orc {
+
+template <class T> struct cx {
+  T re, im;
+  cx() : re(0), im(0) {}
+  cx(T r, T i) : re(r), im(i) {}
+  explicit cx(T r) : re(r), im(0) {}
+};
+
+template <class T> inline cx<T> operator+(cx<T> a, cx<T> b) { return {a.re + b.re, a.im + b.im}; }
+template <class T> inline cx<T> operator-(cx<T> a, cx<T> b) { return {a.re - b.re, a.im - b.im}; }
+template <class T> inline cx<T> operator-(cx<T> a) { return {-a.re, -a.im}; }
+// complex*complex, plain 4-multiply form (GCC tree-complex, Fortran rules)
+template <class T> inline cx<T> operator*(cx<T> a, cx<T> b) {
+  return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+}
+// complex/complex, GCC expand_complex_div_wide (Smith, no rescue)
+template <class T> inline cx<T> operator/(cx<T> a, cx<T> b) {
+  if (std::fabs(b.re) < std::fabs(b.im)) {
+    T ratio = b.re / b.im;
+    T div = (b.re * ratio) + b.im;
+    T tr = (a.re * ratio) + a.im;
+    T ti = (a.im * ratio) - a.re;
+    return {tr / div, ti / div};
+  } else {
+    T ratio = b.im / b.re;
+    T div = (b.im * ratio) + b.re;
+    T tr = (a.im * ratio) + a.re;
+    T ti = a.im - (a.re * ratio);
+    return {tr / div, ti / div};
+  }
+}
+// mixed real/complex: Fortran converts the real operand to complex first
+template <class T> inline cx<T> operator*(cx<T> a, T x) { return a * cx<T>(x, T(0)); }
+template <class T> inline cx<T> operator*(T x, cx<T> a) { return cx<T>(x, T(0)) * a; }
+template <class T> inline cx<T> operator/(cx<T> a, T x) { return a / cx<T>(x, T(0)); }
+template <class T> inline cx<T> operator/(T x, cx<T> a) { return cx<T>(x, T(0)) / a; }
+template <class T> inline cx<T> operator+(cx<T> a, T x) { return {a.re + x, a.im + T(0)}; }
+template <class T> inline cx<T> operator+(T x, cx<T> a) { return {x + a.re, T(0) + a.im}; }
+template <class T> inline cx<T> operator-(T x, cx<T> a) { return {x - a.re, T(0) - a.im}; }
+template <class T> inline cx<T> operator-(cx<T> a, T x) { return {a.re - x, a.im - T(0)}; }
+template <class T> inline cx<T> conj(cx<T> a) { return {a.re, -a.im}; }
+
+// ---- libm bindings (double -> glibc double routines, long double -> *l) ----
+template <class T> struct lm;
+template <> struct lm<double> {
+  typedef double _Complex C;
+  static C mk(cx<double> z) { C c; __real__ c = z.re; __imag__ c = z.im; return c; }
+  static cx<double> un(C c) { return {__real__ c, __imag__ c}; }
+  static cx<double> sqrt(cx<double> z) { return un(::csqrt(mk(z))); }
+  static cx<double> cosh(cx<double> z) { return un(::ccosh(mk(z))); }
+  static cx<double> sinh(cx<double> z) { return un(::csinh(mk(z))); }
+  static cx<double> exp(cx<double> z) { return un(::cexp(mk(z))); }
+  static cx<double> log(cx<double> z) { return un(::clog(mk(z))); }
+  static double abs(cx<double> z) { return ::cabs(mk(z)); }
+  static double j0(double x) { return ::j0(x); }
+  static double j1(double x) { return ::j1(x); }
+  static double lgamma(double x) { return ::lgamma(x); }
+};
+template <> struct lm<long double> {
+  typedef long double _Complex C;
+  static C mk(cx<long double> z) { C c; __real__ c = z.re; __imag__ c = z.im; return c; }
+  static cx<long double> un(C c) { return {__real__ c, __imag__ c}; }
+  static cx<long double> sqrt(cx<long double> z) { return un(::csqrtl(mk(z))); }
+  static cx<long double> cosh(cx<long double> z) { return un(::ccoshl(mk(z))); }
+  static cx<long double> sinh(cx<long double> z) { return un(::csinhl(mk(z))); }
+  static cx<long double> exp(cx<long double> z) { return un(::cexpl(mk(z))); }
+  static cx<long double> log(cx<long double> z) { return un(::clogl(mk(z))); }
+  static long double abs(cx<long double> z) { return ::cabsl(mk(z)); }
+  static long double j0(long double x) { return ::j0l(x); }
+  static long double j1(long double x) { return ::j1l(x); }
+  static long double lgamma(long double x) { return ::lgammal(x); }
+};
+
+template <class T> inline cx<T> csqrt(cx<T> z) { return lm<T>::sqrt(z); }
+template <class T> inline cx<T> ccosh(cx<T> z) { return lm<T>::cosh(z); }
+template <class T> inline cx<T> csinh(cx<T> z) { return lm<T>::sinh(z); }
+template <class T> inline cx<T> cexp(cx<T> z) { return lm<T>::exp(z); }
+template <class T> inline cx<T> clog(cx<T> z) { return lm<T>::log(z); }
+template <class T> inline T cabs(cx<T> z) { return lm<T>::abs(z); }
+
+// utility.f90:59-64  is_finite: .not.(isnan(abs(x)) .or. abs(x) > huge(abs(x)))
+template <class T> inline bool is_finite(cx<T> z) {
+  T a = cabs(z);
+  return !(std::isnan(a) || a > std::numeric_limits<T>::max());
+}
+
+}  // namespace orc
