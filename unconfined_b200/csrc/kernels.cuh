@@ -1,0 +1,675 @@
+// sm_100a kernels for the Laplace-Hankel drawdown hot path (driver.f90:100-231 of the
+// reference behind one launch).  FP64 CUDA-core work: no tensor cores (not a dense
+// contraction), HBM traffic is ~40 B per point against ~1e7 FLOP, so the bound is the
+// FP64 pipe.  See DESIGN.md for the layout; in short, per CTA = one (t,r) column and
+// a tile of ZT z-values:
+//   prologue  threads build the per-p tables (de Hoog p, lapTime, Moench / storage
+//             factors) and the per-abscissa tables (a^2 and weight*a*J0(a rD)) in
+//             shared memory;
+//   phase A   one warp per p: lanes split the tanh-sinh nodes (Richardson folded into
+//             one weight per node) and the Gauss-Lobatto nodes (contiguous blocks so a
+//             lane touches at most two J0 intervals); partial sums are reduced with
+//             warp shuffles;
+//   phase B   one thread per (p,z): Wynn-epsilon on the interval areas;
+//   phase C   one warp per (z, value|derivative): de Hoog q-d + continued fraction.
+#pragma once
+#include <cstdint>
+#include "cmath.cuh"
+
+namespace unc {
+
+#define UNC_MAX_NACC 32
+#define UNC_WARPS 8
+#define UNC_THREADS (UNC_WARPS * 32)
+
+struct DevParams {
+  int model, M, np, N, R, G, nacc, gl_rounds, nts_pad, time_type, n_time_par, moench_M, n_j0z;
+  double alpha, log_tol, tee_mult, kappa, alphaD, beta, lD, dD, bD, rDw, CDw, tDb, lD1, dD1;
+  const double *ts_T;          // [N]   tanh(u2)+1           (integration.f90:62)
+  const double *ts_wc;         // [N]   Richardson-combined tanh-sinh weights
+  const double *gl_x;          // [G]   Gauss-Lobatto interior nodes
+  const double *gl_w;          // [G]
+  const double *j0z;           // [n_j0z]
+  const double *time_par;      // [n_time_par]
+  const double *moench_gamma;  // [moench_M]
+};
+
+struct Job {
+  long long ncol;   // number of (t,r) columns (grid) or points
+  int nz;           // z-values per column
+  long long tdiv;   // column c uses tD[c / tdiv], sv[c / tdiv]
+  long long rmod;   // and rD[c % rmod]
+  int zstride;      // z of column c starts at zD + c*zstride (0: shared grid z, 1: points)
+  const double *tD;
+  const int *sv;
+  const double *rD;
+  const double *zD;
+  const int *zLay;
+  const double *ts_scale;  // per column, or NULL (fresh abscissae)
+  double *s, *ds;
+  int *flags;
+};
+
+// ---------------------------------------------------------------------------
+// time.f90:34-124  lapTime(p) for one p (all behaviours; literal operation order)
+__device__ __noinline__ cplx laptime_dev(const DevParams &P, cplx p) {
+  const double *par = P.time_par;  // par[i-1] = timePar(i)
+  const int tt = P.time_type;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  if (tt == 1) return cexp_g((-par[0]) * p) / p;
+  if (tt == 2) return cexp_g((-par[0]) * p) / p - cexp_g((-par[1]) * p) / p;
+  if (tt == 3) return cexp_g((-par[0]) * p);
+  if (tt == 4) return 1.0 / (p - p * cexp_g((-par[0]) * p)) * (1.0 - cexp_g((-par[1]) * p)) / p;
+  if (tt == 5) return cexp_g((-par[1]) * p) / (p + p * cexp_g((-par[0]) * p));
+  if (tt == 6) return cexp_g((-par[1]) * p) * p / (p * p + par[0] * par[0]);
+  if (tt == 7) {
+    // numerator is exp(x)-exp(x) as written in the reference (time.f90:72-74)
+    cplx e1 = cexp_g(par[0] * p);
+    return cexp_g((-par[1]) * p) / (p * p) * (e1 - e1) / (e1 + e1);
+  }
+  if (tt == 8) {
+    cplx eh = cexp_g((-par[0]) * p / 2.0);
+    return cexp_g((-par[1]) * p) * (1.0 - eh) / ((1.0 + eh) * p);
+  }
+  if (tt < 0 && tt >= -100) {
+    const int n = -tt;
+    const double tf = par[n];
+    cplx s = mk(0.0, 0.0);
+    double sq = 0.0, qprev = 0.0;
+    for (int i = 1; i <= n; ++i) {
+      double q = par[n + i];
+      s = s + (q - qprev) * cexp_g((-par[i - 1]) * p);
+      sq += q - qprev;
+      qprev = q;
+    }
+    return (s - sq * cexp_g((-tf) * p)) / p;
+  }
+  if (tt <= -101) {
+    const int n = -tt - 100;
+    const double tf = par[n];
+    cplx s = mk(0.0, 0.0);
+    double sw = 0.0, wprev = 0.0;
+    for (int i = 1; i <= n; ++i) {
+      double ti = par[i - 1];
+      double tnext = (i < n) ? par[i] : tf;
+      double yi = par[n + i];
+      double ynext = (i < n) ? par[n + i + 1] : 0.0;  // y(n+1) is out of bounds in the reference
+      double W = (ynext - yi) / (tnext - ti);
+      s = s + (W - wprev) * cexp_g((-ti) * p);
+      sw += W - wprev;
+      wprev = W;
+    }
+    return (s - sw * cexp_g((-tf) * p)) / (p * p);
+  }
+  return mk(nan, nan);
+}
+
+// ---------------------------------------------------------------------------
+// cbessel.f90:877-1146 (cbesk) -> 5036-5495 (cbknu) for fnu=0, kode=1, n=2, Re z >= 0.
+// K[0]=K0(z), K[1]=K1(z).  Out-of-range arguments give NaN (the reference prints ierr
+// and carries on with whatever cy holds, laplace_hankel_solutions.f90:259-262).
+__device__ __noinline__ void cbesk01_dev(cplx z, cplx *K) {
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  const double tol = 2.220446049250313e-16;
+  const double r1m5 = 0.30102999566398120;  // log10(2)
+  const double elim = 2.303 * (1021 * r1m5 - 3.0);
+  const double alim = elim + fmax(-(r1m5 * 52) * 2.303, -41.45);
+  const double pi = 3.141592653589793, hpi = 1.5707963267948966;
+  const double rthpi = 1.2533141373155001;   // sqrt(8 atan 1)/2
+  const double spi = 1.9098593171027440;     // 3/(2 atan 1)
+  const double fpi = 1.89769999331517738, tth = 6.66666666666666666e-01;
+  const double xx = z.re, yy = z.im;
+  const double caz = hypot(xx, yy);
+  K[0] = mk(nan, nan); K[1] = mk(nan, nan);
+  if (!(caz <= fmin(0.5 / tol, 2147483647.0 * 0.5)) || !(caz >= DBL_MIN * 1.0e3) || !(xx >= 0.0)) return;
+  const cplx rz = mk(2.0, 0.0) / z;
+  cplx s1, s2;
+  double csr = 1.0;
+  if (caz <= 2.0) {
+    // power series, cbessel.f90:5098-5200 with dnu=0: fc=1, t1=t2=1, g1=-cc(1), g2=1
+    cplx smu = clog_g(rz);
+    cplx f = mk(-5.77215664901532861e-01, 0.0) + smu;  // g1*cch + smu*g2, cch=(1,0)
+    cplx p = mk(0.5, 0.0), q = mk(0.5, 0.0);
+    s1 = f;
+    s2 = p;
+    double ak = 1.0, a1 = 1.0, bk = 1.0;
+    cplx ck = mk(1.0, 0.0);
+    if (caz >= tol) {
+      cplx cz = z * z * 0.25;
+      double t1 = 0.25 * caz * caz;
+      do {
+        f = (f * ak + p + q) / bk;
+        p = p / ak;
+        q = q / ak;
+        double rk = 1.0 / ak;
+        ck = ck * cz * rk;
+        s1 = s1 + ck * f;
+        s2 = s2 + ck * (p - f * ak);
+        a1 = a1 * t1 * rk;
+        bk = bk + ak + ak + 1.0;
+        ak = ak + 1.0;
+      } while (a1 > tol);
+    }
+    double css = 1.0;
+    if (fabs(smu.re) > alim) { css = tol; csr = 1.0 / tol; }  // kflag=3
+    cplx p2 = s2 * mk(css, 0.0);
+    s2 = p2 * rz;
+    s1 = s1 * mk(css, 0.0);
+  } else {
+    // Miller backward recurrence, cbessel.f90:5209-5327
+    if (xx > alim) return;  // exp(-z) underflow branch (ckscl) not implemented: NaN
+    cplx coef = mk(rthpi, 0.0) / csqrt_g(z);
+    {
+      double a1 = exp(-xx);
+      cplx pt = a1 * mk(cos(yy), -sin(yy));
+      coef = coef * pt;
+    }
+    double ak = 1.0;  // |cos(pi*dnu)|
+    double fhs = 0.25;
+    double t1 = 52 * r1m5 * 3.321928094;
+    t1 = fmin(fmax(t1, 12.0), 60.0);
+    double t2 = tth * t1 - 6.0;
+    if (fabs(xx) * 2.0 < DBL_MIN) t1 = hpi;
+    else t1 = fabs(atan(yy / xx));
+    double fk;
+    if (t2 <= caz) {
+      double etest = ak / (pi * caz * tol);
+      fk = 1.0;
+      if (!(etest < 1.0)) {
+        double fks = 2.0, rk = caz + caz + 2.0, a1 = 0.0, a2 = 1.0;
+        bool found = false;
+        for (int i = 1; i <= 30; ++i) {
+          ak = fhs / fks;
+          double bk = rk / (fk + 1.0);
+          double tm = a2;
+          a2 = bk * a2 - ak * a1;
+          a1 = tm;
+          rk = rk + 2.0;
+          fks = fks + fk + fk + 2.0;
+          fhs = fhs + fk + fk;
+          fk = fk + 1.0;
+          tm = fabs(a2) * fk;
+          if (etest < tm) { found = true; break; }
+        }
+        if (!found) return;
+        fk = fk + spi * t1 * sqrt(t2 / caz);
+        fhs = 0.25;
+      }
+    } else {
+      double a2 = sqrt(caz);
+      ak = fpi * ak / (tol * sqrt(a2));
+      double aa = 3.0 * t1 / (1.0 + caz);
+      double bb = 14.7 * t1 / (28.0 + caz);
+      ak = (log(ak) + caz * cos(aa) / (1.0 + 0.008 * caz)) / cos(bb);
+      fk = 0.12125 * ak * ak / caz + 1.5;
+    }
+    int k = (int)fk;
+    fk = k;
+    double fks = fk * fk;
+    cplx p1 = mk(0.0, 0.0), p2 = mk(tol, 0.0), cs = p2;
+    for (int i = 1; i <= k; ++i) {
+      double a1 = fks - fk;
+      double a2 = (fks + fk) / (a1 + fhs);
+      double rk = 2.0 / (fk + 1.0);
+      double tt1 = (fk + xx) * rk;
+      double tt2 = yy * rk;
+      cplx pt = p2;
+      p2 = (p2 * mk(tt1, tt2) - p1) * a2;
+      p1 = pt;
+      cs = cs + p2;
+      fks = a1 - fk + 1.0;
+      fk = fk - 1.0;
+    }
+    double tm = cabs_d(cs);
+    cplx pt = mk(1.0 / tm, 0.0);
+    s1 = pt * p2;
+    cs = conj(cs) * pt;
+    s1 = coef * s1 * cs;
+    tm = cabs_d(p2);
+    pt = mk(1.0 / tm, 0.0);
+    p1 = pt * p1;
+    p2 = conj(p2) * pt;
+    pt = p1 * p2;
+    s2 = s1 * (mk(1.0, 0.0) + (mk(0.5, 0.0) - pt) / z);
+  }
+  K[0] = s1 * mk(csr, 0.0);
+  K[1] = s2 * mk(csr, 0.0);
+}
+
+// ---------------------------------------------------------------------------
+// Per-p shared tables
+struct PTab {
+  cplx *p;    // de Hoog abscissae (invlap.f90:166-170)
+  cplx *lt;   // lapTime(p)
+  cplx *aux;  // model 3: sum_m 1/(1+p/gamma_m); model 2: uDf numerator A0/(p*tDb+1) parts
+  cplx *aux2; // model 2: (p*tDb + 1)
+};
+
+// laplace_hankel_solutions.f90:133-202 (hantush) for one (a,p) and a tile of z;
+// also the layer-3 value at zD=1 when want_top (called from models 3/5, :81,162-170).
+// Literal operation order; u[] excludes nothing: it is udp*theis/bD.
+template <int ZT>
+__device__ __forceinline__ void hantush_literal(const DevParams &P, double a2, cplx p, cplx eta,
+                                                const double *z, const int *lay, int nzt,
+                                                bool want_top, cplx *u, cplx *utop,
+                                                bool storage_variant) {
+  const cplx ff1 = csinh_g(eta * P.dD);
+  const cplx ff2 = csinh_g(eta * P.lD1);
+  const cplx sh = csinh_g(eta);
+  bool any1 = false;
+#pragma unroll
+  for (int i = 0; i < ZT; ++i) if (i < nzt && lay[i] == 1) any1 = true;
+  cplx g3 = mk(0.0, 0.0);
+  if (any1) g3 = cexp_g((-eta) * P.lD1) - (ff1 + cexp_g(-eta) * ff2) / sh;
+  const cplx th = 2.0 / (p + a2);
+#pragma unroll
+  for (int i = 0; i < ZT; ++i) {
+    if (i < nzt) {
+      cplx v;
+      if (lay[i] == 1) {
+        v = g3 * ccosh_g(eta * z[i]);
+      } else {
+        cplx g2 = (ff1 * ccosh_g(eta * z[i]) + ff2 * ccosh_g(eta * (1.0 - z[i]))) / sh;
+        if (lay[i] == 2) v = 1.0 - g2;
+        else v = ccosh_g(eta * (P.dD1 - z[i])) - g2;
+      }
+      u[i] = storage_variant ? v : v * th / P.bD;
+    }
+  }
+  if (want_top) {
+    cplx g1 = ccosh_g(eta * (P.dD1 - 1.0));
+    cplx g2 = (ff1 * ccosh_g(eta * 1.0) + ff2 * ccosh_g(eta * (1.0 - 1.0))) / sh;
+    *utop = (g1 - g2) * th / P.bD;
+  }
+}
+
+// laplace_hankel_solutions.f90:30-116: fp(p, z-tile) at one abscissa, WITHOUT the common
+// factor a*J0(a rD)*lapTime(p) of :118 (folded into the quadrature weight / applied per p).
+template <int ZT>
+__device__ __forceinline__ void soln_literal(const DevParams &P, const PTab &T, int pi, double a2,
+                                             const double *z, const int *lay, int nzt, cplx *f) {
+  const cplx p = T.p[pi];
+  const int model = P.model;
+  if (model == 0) {
+    cplx th = 2.0 / (p + a2);
+#pragma unroll
+    for (int i = 0; i < ZT; ++i) f[i] = th;
+    return;
+  }
+  const cplx eta = csqrt_g((p + a2) / P.kappa);
+  if (model == 1) {
+    cplx dummy;
+    hantush_literal<ZT>(P, a2, p, eta, z, lay, nzt, false, f, &dummy, false);
+    return;
+  }
+  if (model == 2) {
+    // :204-301  u = (uDf/bD)*uDp,  uDf = A0/((p+a^2)*(p*tDb+1))
+    cplx dummy, uDp[ZT];
+    hantush_literal<ZT>(P, a2, p, eta, z, lay, nzt, false, uDp, &dummy, true);
+    cplx uDf = T.aux[pi] / ((p + a2) * T.aux2[pi]);
+    cplx pre = uDf / P.bD;
+#pragma unroll
+    for (int i = 0; i < ZT; ++i) if (i < nzt) f[i] = pre * uDp[i];
+    return;
+  }
+  // models 3,4,5  (:64-93)
+  cplx xi = eta * P.alphaD / p;
+  if (model == 3) xi = xi * (double)P.moench_M / T.aux[pi];
+  cplx udp[ZT], top;
+  if (model == 4) {
+    cplx th = 2.0 / (p + a2);
+#pragma unroll
+    for (int i = 0; i < ZT; ++i) udp[i] = th;
+    top = th;
+  } else {
+    hantush_literal<ZT>(P, a2, p, eta, z, lay, nzt, true, udp, &top, false);
+  }
+  const double MAXEXP = 12.014551129705717;  // -log(epsilon(1d0))/3  (constants.f90:66)
+  if (eta.re < MAXEXP) {
+    cplx den = (1.0 + P.beta * eta * xi) * ccosh_g(eta) + xi * csinh_g(eta);
+#pragma unroll
+    for (int i = 0; i < ZT; ++i)
+      if (i < nzt) f[i] = udp[i] - top * ccosh_g(eta * z[i]) / den;
+  } else {
+    cplx den = 1.0 + P.beta * eta * xi + xi;
+#pragma unroll
+    for (int i = 0; i < ZT; ++i)
+      if (i < nzt) f[i] = udp[i] - top * cexp_g(eta * (z[i] - 1.0)) / den;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// integration.f90:125-189  wynn_epsilon on nacc terms (two live columns, in place)
+__device__ __noinline__ cplx wynn_dev(const cplx *series, int nacc) {
+  cplx X[UNC_MAX_NACC + 1], Y[UNC_MAX_NACC + 1];  // 1-based; X: odd columns (starts as col -1), Y: even
+  int ns = nacc;
+  cplx run = mk(0.0, 0.0);
+  for (int i = 1; i <= nacc; ++i) {
+    if (!is_finite_c(series[i - 1])) {
+      ns = i - 1;
+      break;
+    }
+    run = run + series[i - 1];
+    Y[i] = run;
+    X[i] = mk(0.0, 0.0);
+  }
+  if (ns < nacc && ns < 4) return mk(-999999.875, 0.0);  // real(4) literal -999999.9
+  const double eps = 2.220446049250313e-16;
+  for (int j = 0; j <= ns - 2; ++j) {
+    cplx *cur = (j & 1) ? X : Y;   // column j
+    cplx *oth = (j & 1) ? Y : X;   // column j-1 -> becomes j+1
+    for (int m = 1; m <= ns - (j + 1); ++m) {
+      cplx denom = cur[m + 1] - cur[m];
+      if (cabs_d(denom) > eps) oth[m] = oth[m + 1] + 1.0 / denom;
+      else return cur[m + 1];
+    }
+  }
+  return Y[2];
+}
+
+// ---------------------------------------------------------------------------
+// invlap.f90:46-141  de Hoog, Knight & Stokes for one time, executed by one warp.
+// f: np=2M+1 transform values (shared, stride fstride); if pmul != NULL each value is
+// multiplied by p first (driver.f90:228).  q,e,d: per-warp scratch of np complex each.
+__device__ __noinline__ double dehoog_warp(const DevParams &P, const cplx *f, int fstride,
+                                           const cplx *pmul, double t, double tee, cplx *q,
+                                           cplx *e, cplx *d, int lane) {
+  const int M = P.M, n2 = 2 * M;
+  const unsigned full = 0xffffffffu;
+  double mx = -1.0;
+  bool anynum = false;
+  for (int i = lane; i <= n2; i += 32) {
+    cplx v = f[i * fstride];
+    if (pmul) v = v * pmul[i];
+    double a = hypot(v.re, v.im);
+    if (!isnan(a)) { anynum = true; mx = fmax(mx, a); }
+    if (isnan(v.re) || isnan(v.im)) v = mk(0.0, 0.0);
+    d[i] = v;              // f for now
+    e[i] = mk(0.0, 0.0);   // e(:,0) = 0
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(full, mx, o));
+  anynum = __any_sync(full, anynum);
+  __syncwarp();
+  if (!anynum || !(mx > DBL_MIN)) return 0.0;
+  // q(:,1)
+  for (int i = lane; i <= n2 - 1; i += 32) {
+    if (i == 0) q[0] = d[1] / (d[0] / 2.0);
+    else q[i] = d[i + 1] / d[i];
+  }
+  __syncwarp();
+  if (lane == 0) d[0] = d[0] / 2.0;
+  for (int r = 1; r <= M; ++r) {
+    int mxi = 2 * (M - r);
+    cplx t0 = mk(0, 0), t1 = mk(0, 0);
+    if (lane <= mxi) t0 = q[lane + 1] - q[lane] + e[lane + 1];
+    if (lane + 32 <= mxi) t1 = q[lane + 33] - q[lane + 32] + e[lane + 33];
+    __syncwarp();
+    if (lane <= mxi) e[lane] = t0;
+    if (lane + 32 <= mxi) e[lane + 32] = t1;
+    if (lane == 0) d[2 * r - 1] = -q[0];
+    __syncwarp();
+    if (lane == 0) d[2 * r] = -e[0];
+    if (r != M) {
+      mxi = 2 * (M - (r + 1)) + 1;
+      if (lane <= mxi) t0 = q[lane + 1] * e[lane + 1] / e[lane];
+      if (lane + 32 <= mxi) t1 = q[lane + 33] * e[lane + 33] / e[lane + 32];
+      __syncwarp();
+      if (lane <= mxi) q[lane] = t0;
+      if (lane + 32 <= mxi) q[lane + 32] = t1;
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  // z = exp(i*pi*t/tee)   (invlap.f90:110)
+  const double PI = 3.141592653589793;
+  double sn, cs;
+  sincos_g((PI * t) / tee, &sn, &cs);
+  const cplx zz = mk(cs, sn);
+  cplx Am2 = mk(0.0, 0.0), Am1 = d[0], Bm2 = mk(1.0, 0.0), Bm1 = mk(1.0, 0.0);
+  for (int n = 1; n <= n2 - 1; ++n) {
+    cplx dn = d[n];
+    cplx An = Am1 + dn * Am2 * zz;
+    cplx Bn = Bm1 + dn * Bm2 * zz;
+    Am2 = Am1; Am1 = An; Bm2 = Bm1; Bm1 = Bn;
+  }
+  cplx brem = (1.0 + (d[n2 - 1] - d[n2]) * zz) / 2.0;
+  cplx rem = (-brem) * (1.0 - csqrt_g(1.0 + d[n2] * zz / (brem * brem)));
+  cplx A2M = Am1 + rem * Am2;
+  cplx B2M = Bm1 + rem * Bm2;
+  const double gamma = P.alpha - P.log_tol / (2.0 * tee);
+  return exp(gamma * t) / tee * (A2M / B2M).re;
+}
+
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double shfl_down_d(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double shfl_xor_d(double v, int d) { return __shfl_xor_sync(0xffffffffu, v, d); }
+
+// shared-memory carve-up (bytes) for a given parameter set
+__host__ __device__ inline size_t smem_bytes(int np, int nacc, int na, int ZT) {
+  size_t b = 0;
+  b += (size_t)4 * np * sizeof(cplx);                 // p, lt, aux, aux2
+  b += (size_t)2 * na * sizeof(double);               // a2, wj
+  size_t areas = (size_t)np * ZT * nacc * sizeof(cplx);
+  size_t scratch = (size_t)UNC_WARPS * 3 * np * sizeof(cplx);  // de Hoog q,e,d per warp (aliases areas)
+  b += areas > scratch ? areas : scratch;
+  b += (size_t)np * ZT * sizeof(cplx);                // finint -> totlap
+  b += (size_t)ZT * (sizeof(double) + 2 * sizeof(int));  // z, lay, flags
+  return (b + 15) & ~(size_t)15;
+}
+
+template <int ZT>
+__global__ void __launch_bounds__(UNC_THREADS)
+lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job J) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int np = P.np, nacc = P.nacc, G = P.G;
+  const int na = P.nts_pad + P.gl_rounds * 32;
+  const int ntiles = (J.nz + ZT - 1) / ZT;
+  const long long col = blockIdx.x / ntiles;
+  const int tile = (int)(blockIdx.x % ntiles);
+  const int z0 = tile * ZT;
+  const int nzt = min(ZT, J.nz - z0);
+
+  // carve shared memory
+  unsigned char *sp = smem_raw;
+  PTab T;
+  T.p = (cplx *)sp; sp += np * sizeof(cplx);
+  T.lt = (cplx *)sp; sp += np * sizeof(cplx);
+  T.aux = (cplx *)sp; sp += np * sizeof(cplx);
+  T.aux2 = (cplx *)sp; sp += np * sizeof(cplx);
+  double *s_a2 = (double *)sp; sp += na * sizeof(double);
+  double *s_wj = (double *)sp; sp += na * sizeof(double);
+  cplx *s_area = (cplx *)sp;
+  {
+    size_t areas = (size_t)np * ZT * nacc * sizeof(cplx);
+    size_t scratch = (size_t)UNC_WARPS * 3 * np * sizeof(cplx);
+    sp += areas > scratch ? areas : scratch;
+  }
+  cplx *s_fin = (cplx *)sp; sp += (size_t)np * ZT * sizeof(cplx);
+  double *s_z = (double *)sp; sp += ZT * sizeof(double);
+  int *s_lay = (int *)sp; sp += ZT * sizeof(int);
+  int *s_flag = (int *)sp;
+
+  const double tD = J.tD[col / J.tdiv];
+  const int sv = J.sv[col / J.tdiv];
+  const double rD = J.rD[col % J.rmod];
+  const double tee = P.tee_mult * tD;
+  const double arg = P.j0z[sv - 1] / rD;                      // driver.f90:120
+  const double tscale = J.ts_scale ? J.ts_scale[col] : arg;  // driver.f90:121-126
+  const double *zsrc = J.zD + (J.zstride ? col * (long long)J.nz : 0) + z0;
+  const int *lsrc = J.zLay + (J.zstride ? col * (long long)J.nz : 0) + z0;
+
+  // ---- prologue -------------------------------------------------------------
+  if (tid < ZT) {
+    s_z[tid] = (tid < nzt) ? zsrc[tid] : 0.0;
+    s_lay[tid] = (tid < nzt) ? lsrc[tid] : 2;
+    s_flag[tid] = 0;
+  }
+  for (int i = tid; i < np; i += UNC_THREADS) {
+    // invlap.f90:166-170
+    const double PI = 3.141592653589793;
+    double sigma = P.alpha - P.log_tol / (2.0 * tee);
+    cplx p = mk(sigma, PI * (double)i / tee);
+    T.p[i] = p;
+    T.lt[i] = laptime_dev(P, p);
+    cplx aux = mk(0.0, 0.0), aux2 = mk(0.0, 0.0);
+    if (P.model == 3) {
+      // sum(1/(1 + p .X. 1/gamma), dim=2)   laplace_hankel_solutions.f90:74
+      for (int m = 0; m < P.moench_M; ++m) aux = aux + 1.0 / (1.0 + p * (1.0 / P.moench_gamma[m]));
+    } else if (P.model == 2) {
+      // :253-266  xi = rDw*sqrt(p); A0 = 2/(p*CDw*K0 + xi*K1)
+      cplx xi = P.rDw * csqrt_g(p);
+      cplx K[2];
+      cbesk01_dev(xi, K);
+      aux = 2.0 / (p * P.CDw * K[0] + xi * K[1]);
+      aux2 = p * P.tDb + 1.0;
+    }
+    T.aux[i] = aux;
+    T.aux2[i] = aux2;
+  }
+  for (int idx = tid; idx < na; idx += UNC_THREADS) {
+    double a = 0.0, w = 0.0;
+    if (idx < P.nts_pad) {
+      if (idx < P.N) {
+        a = (P.ts_T[idx] * tscale) / 2.0;  // integration.f90:62
+        w = P.ts_wc[idx] * (arg / 2.0);    // driver.f90:135,154 + Richardson (linear in tmp)
+      }
+    } else {
+      const int k = idx - P.nts_pad;
+      const int L = k & 31, i = k >> 5;
+      const int node = L * P.gl_rounds + i;
+      if (node < nacc * G) {
+        const int j = node / G, m = node - j * G;
+        const double lob = P.j0z[sv + j - 1] / rD;  // driver.f90:188-193
+        const double hib = P.j0z[sv + j] / rD;
+        const double width = hib - lob;
+        a = fma(width, P.gl_x[m], hib + lob) / 2.0;
+        w = P.gl_w[m] * (width / 2.0);
+      }
+    }
+    s_a2[idx] = a * a;
+    s_wj[idx] = (w != 0.0) ? w * (a * j0_dev(a * rD)) : 0.0;  // laplace_hankel_solutions.f90:118
+  }
+  __syncthreads();
+
+  // ---- phase A: Hankel quadrature sums, one warp per p ------------------------
+  const int rounds = P.gl_rounds;
+  const int node0 = lane * rounds;
+  const int jA = node0 / G;
+  const int iB = (jA + 1) * G - node0;  // first round that falls in interval jA+1
+  const int jA_valid = (node0 < nacc * G) ? jA : -1 - lane;  // distinct ids for empty lanes
+  double zt[ZT];
+  int lt_[ZT];
+#pragma unroll
+  for (int i = 0; i < ZT; ++i) { zt[i] = s_z[i]; lt_[i] = s_lay[i]; }
+
+  for (int pi = warp; pi < np; pi += UNC_WARPS) {
+    cplx accT[ZT], accA[ZT], accB[ZT];
+#pragma unroll
+    for (int i = 0; i < ZT; ++i) { accT[i] = mk(0, 0); accA[i] = mk(0, 0); accB[i] = mk(0, 0); }
+    cplx f[ZT];
+    for (int i = 0; i < P.nts_pad / 32; ++i) {
+      const int idx = i * 32 + lane;
+      const double w = s_wj[idx];
+      if (idx < P.N) {
+        soln_literal<ZT>(P, T, pi, s_a2[idx], zt, lt_, nzt, f);
+#pragma unroll
+        for (int k = 0; k < ZT; ++k) accT[k] = fma_acc(w, f[k], accT[k]);
+      }
+    }
+    for (int i = 0; i < rounds; ++i) {
+      const int idx = P.nts_pad + i * 32 + lane;
+      const double w = s_wj[idx];
+      if (node0 + i < nacc * G) {
+        soln_literal<ZT>(P, T, pi, s_a2[idx], zt, lt_, nzt, f);
+        if (i < iB) {
+#pragma unroll
+          for (int k = 0; k < ZT; ++k) accA[k] = fma_acc(w, f[k], accA[k]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < ZT; ++k) accB[k] = fma_acc(w, f[k], accB[k]);
+        }
+      }
+    }
+    // reductions
+    cplx *area_p = s_area + (size_t)pi * ZT * nacc;
+    for (int k = lane; k < ZT * nacc; k += 32) area_p[k] = mk(0.0, 0.0);
+#pragma unroll
+    for (int k = 0; k < ZT; ++k) {
+      double tr = accT[k].re, ti = accT[k].im;
+      for (int o = 16; o > 0; o >>= 1) { tr += shfl_xor_d(tr, o); ti += shfl_xor_d(ti, o); }
+      if (lane == 0) s_fin[pi * ZT + k] = mk(tr, ti);
+      double ar = accA[k].re, ai = accA[k].im;
+      for (int dlt = 1; dlt < 32; dlt <<= 1) {
+        double orr = shfl_down_d(ar, dlt), oi = shfl_down_d(ai, dlt);
+        int oj = __shfl_down_sync(0xffffffffu, jA_valid, dlt);
+        if (lane + dlt < 32 && oj == jA_valid) { ar += orr; ai += oi; }
+      }
+      int prevj = __shfl_up_sync(0xffffffffu, jA_valid, 1);
+      bool head = (jA_valid >= 0) && (lane == 0 || prevj != jA_valid);
+      __syncwarp();
+      if (head) area_p[k * nacc + jA] = mk(ar, ai);
+      __syncwarp();
+      if (iB < rounds && jA_valid >= 0 && jA + 1 < nacc) {
+        cplx cur = area_p[k * nacc + jA + 1];
+        area_p[k * nacc + jA + 1] = mk(cur.re + accB[k].re, cur.im + accB[k].im);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase B: Wynn-epsilon per (p,z), totlap = finint + infint ---------------
+  for (int k = tid; k < np * ZT; k += UNC_THREADS) {
+    const int pi = k / ZT, zi = k - pi * ZT;
+    if (zi < nzt) {
+      const double nan = __longlong_as_double(0x7ff8000000000000LL);
+      const cplx lt = T.lt[pi];
+      cplx series[UNC_MAX_NACC];
+      bool any = false;
+      for (int j = 0; j < nacc; ++j) {
+        cplx a = s_area[((size_t)pi * ZT + zi) * nacc + j];
+        a = is_finite_c(a) ? a * lt : mk(nan, nan);
+        series[j] = a;
+        if (cabs_d(a) > 0.0) any = true;   // driver.f90:209
+      }
+      cplx infint = mk(0.0, 0.0);
+      if (any) infint = wynn_dev(series, nacc);
+      else atomicOr(&s_flag[zi], 1);
+      cplx fin = s_fin[k];
+      fin = is_finite_c(fin) ? fin * lt : mk(nan, nan);
+      s_fin[k] = fin + infint;  // totlap, driver.f90:216
+    }
+  }
+  __syncthreads();
+
+  // ---- phase C: de Hoog inversion of value and log-time derivative ------------
+  cplx *scr = s_area + (size_t)warp * 3 * np;
+  for (int job = warp; job < 2 * nzt; job += UNC_WARPS) {
+    const int zi = job >> 1, deriv = job & 1;
+    double v = dehoog_warp(P, s_fin + zi, ZT, deriv ? T.p : nullptr, tD, tee, scr, scr + np,
+                           scr + 2 * np, lane);
+    if (lane == 0) {
+      const long long o = col * (long long)J.nz + z0 + zi;
+      if (deriv) J.ds[o] = v * tD;  // driver.f90:228
+      else {
+        J.s[o] = v;
+        if (J.flags) J.flags[o] = s_flag[zi];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// DFMA-chain microbenchmark: 8 independent chains per thread
+__global__ void fp64_peak_kernel(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+         a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace unc
