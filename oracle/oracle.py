@@ -197,5 +197,29 @@ def soln(prm, a, rD, tD, zD, zLay):
     return out
 
 
+def set_jitter(ulps, seed=0):
+    """Perturb every libm result by up to `ulps` units in the last place (0 = off)."""
+    lib().orc_set_jitter(C.c_double(ulps), C.c_ulonglong(seed))
+
+
+def noise_envelope(fn, nsamples=4, ulps=2.0):
+    """Run fn() (returning (s, ds, ...)) unperturbed and `nsamples` times under jitter;
+    return (s, ds, spread_s, spread_ds) with spread = max |jittered - clean|."""
+    set_jitter(0.0)
+    base = fn()
+    s0, d0 = np.array(base[0]), np.array(base[1])
+    sp_s = np.zeros_like(s0); sp_d = np.zeros_like(d0)
+    try:
+        for k in range(nsamples):
+            set_jitter(ulps, 1000 + k)
+            r = fn()
+            with np.errstate(invalid="ignore"):
+                sp_s = np.fmax(sp_s, np.abs(np.array(r[0]) - s0))
+                sp_d = np.fmax(sp_d, np.abs(np.array(r[1]) - d0))
+    finally:
+        set_jitter(0.0)
+    return s0, d0, sp_s, sp_d
+
+
 def num_threads():
     return lib().orc_num_threads()

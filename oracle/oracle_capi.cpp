@@ -106,6 +106,12 @@ int eval_points_t(const params *prm, int64_t n, const double *tD, const int32_t 
 
 extern "C" {
 
+// ulps = 0 disables; see oracle_math.hpp (jitter)
+void orc_set_jitter(double ulps, unsigned long long seed) {
+  jitter().ulps = ulps;
+  jitter().seed = seed;
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

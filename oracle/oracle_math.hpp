@@ -36,6 +36,27 @@ long double cabsl(long double _Complex) noexcept;
 
 namespace orc {
 
+// ---- optional "other libm" jitter ------------------------------------------
+// When enabled (orc_set_jitter), every result of the glibc routines below is
+// multiplied by (1 + u*ulps*2^-53), u in [-1,1] a hash of the argument bits and a
+// seed.  This emulates an equally valid libm whose last bits differ (the CUDA math
+// library is 1-2 ulp vs glibc's <1 ulp) and is used by the tests to measure, per
+// output point, how far rounding noise alone moves the reference's own result.
+struct jitter_state { double ulps; unsigned long long seed; };
+inline jitter_state &jitter() { static jitter_state j = {0.0, 0ULL}; return j; }
+inline double jitter_u(double a, double b, unsigned salt) {
+  unsigned long long x, y;
+  __builtin_memcpy(&x, &a, 8); __builtin_memcpy(&y, &b, 8);
+  unsigned long long h = x * 0x9E3779B97F4A7C15ULL ^ (y + 0xD1B54A32D192ED03ULL) * 0xBF58476D1CE4E5B9ULL
+                         ^ (jitter().seed + salt) * 0x94D049BB133111EBULL;
+  h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ULL; h ^= h >> 32;
+  return ((double)(h >> 11) * (1.0 / 9007199254740992.0)) * 2.0 - 1.0;
+}
+template <class T> inline T jit(T v, double a, double b, unsigned salt) {
+  if (jitter().ulps == 0.0) return v;
+  return v * (T)(1.0 + jitter_u(a, b, salt) * jitter().ulps * 1.1102230246251565e-16);
+}
+
 template <class T> struct cx {
   T re, im;
   cx() : re(0), im(0) {}
@@ -83,13 +104,23 @@ template <> struct lm<double> {
   typedef double _Complex C;
   static C mk(cx<double> z) { C c; __real__ c = z.re; __imag__ c = z.im; return c; }
   static cx<double> un(C c) { return {__real__ c, __imag__ c}; }
-  static cx<double> sqrt(cx<double> z) { return un(::csqrt(mk(z))); }
-  static cx<double> cosh(cx<double> z) { return un(::ccosh(mk(z))); }
-  static cx<double> sinh(cx<double> z) { return un(::csinh(mk(z))); }
-  static cx<double> exp(cx<double> z) { return un(::cexp(mk(z))); }
+  static cx<double> jc(cx<double> r, cx<double> z, unsigned salt) {
+    return {jit(r.re, z.re, z.im, salt), jit(r.im, z.re, z.im, salt + 1)};
+  }
+  static cx<double> sqrt(cx<double> z) { return jc(un(::csqrt(mk(z))), z, 10); }
+  static cx<double> cosh(cx<double> z) { return jc(un(::ccosh(mk(z))), z, 20); }
+  static cx<double> sinh(cx<double> z) { return jc(un(::csinh(mk(z))), z, 30); }
+  static cx<double> exp(cx<double> z) { return jc(un(::cexp(mk(z))), z, 40); }
   static cx<double> log(cx<double> z) { return un(::clog(mk(z))); }
   static double abs(cx<double> z) { return ::cabs(mk(z)); }
-  static double j0(double x) { return ::j0(x); }
+  // J0: relative jitter plus an absolute one of 0.25 ulp(1)*amplitude (near its zeros
+  // any implementation is only absolutely accurate)
+  static double j0(double x) {
+    double v = ::j0(x);
+    if (jitter().ulps == 0.0) return v;
+    double amp = 1.0 / std::sqrt(1.0 + std::fabs(x));
+    return jit(v, x, 0.0, 50) + 0.25 * jitter_u(x, 1.0, 51) * jitter().ulps * 1.1102230246251565e-16 * amp;
+  }
   static double j1(double x) { return ::j1(x); }
   static double lgamma(double x) { return ::lgamma(x); }
 };

@@ -307,7 +307,32 @@ int launch_zt(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t 
   return UNC_OK;
 }
 
+int launch_grid(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
+  const int NA = P.N + P.nacc * P.G;
+  const size_t smem = unc::grid_smem_bytes(P.np, (NA + 31) & ~31);
+  if (smem > 227 * 1024) return fail(UNC_ERR_UNSUPPORTED, "shared memory need %zu B exceeds 227 KB", smem);
+  DevCtx &c = g_ctx[dev];
+  if (!c.smem_set[8]) {
+    CK(cudaFuncSetAttribute(unc::lh_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    c.smem_set[8] = true;
+  }
+  const long long nblk = J.ncol * ((J.nz + 31) / 32);
+  if (nblk <= 0) return UNC_OK;
+  if (nblk > 2147483647LL) return fail(UNC_ERR_UNSUPPORTED, "too many work items (%lld)", nblk);
+  unc::lh_grid_kernel<<<(unsigned)nblk, UNC_THREADS, smem, st>>>(P, J);
+  g_launches++;
+  CK(cudaGetLastError());
+  return UNC_OK;
+}
+
+// kernel selection: lanes<->z (grid kernel) once a column has enough z to fill most of a
+// warp; otherwise lanes<->abscissae (point kernel).  UNC_FORCE_KERNEL=point|grid overrides.
 int launch(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
+  const char *force = getenv("UNC_FORCE_KERNEL");
+  bool grid = J.nz >= 12;
+  if (force && !strcmp(force, "point")) grid = false;
+  if (force && !strcmp(force, "grid")) grid = true;
+  if (grid) return launch_grid(dev, P, J, st);
   if (J.nz >= 4) return launch_zt<4>(dev, P, J, st);
   if (J.nz >= 2) return launch_zt<2>(dev, P, J, st);
   return launch_zt<1>(dev, P, J, st);

@@ -50,6 +50,10 @@ struct Job {
   int *flags;
 };
 
+}  // namespace unc
+#include "fast.cuh"
+namespace unc {
+
 // ---------------------------------------------------------------------------
 // time.f90:34-124  lapTime(p) for one p (all behaviours; literal operation order)
 __device__ __noinline__ cplx laptime_dev(const DevParams &P, cplx p) {
@@ -338,6 +342,15 @@ __device__ __forceinline__ void soln_literal(const DevParams &P, const PTab &T, 
   }
 }
 
+// Literal evaluation for ONE z (slow path of the fast kernels: Re(eta) beyond the
+// fast-path bound, where the reference's overflow behaviour is part of the contract).
+__device__ __noinline__ cplx soln_literal_one(const DevParams &P, const PTab &T, int pi, double a2,
+                                              double z, int lay) {
+  cplx f[1];
+  soln_literal<1>(P, T, pi, a2, &z, &lay, 1, f);
+  return f[0];
+}
+
 // ---------------------------------------------------------------------------
 // integration.f90:125-189  wynn_epsilon on nacc terms (two live columns, in place)
 __device__ __noinline__ cplx wynn_dev(const cplx *series, int nacc) {
@@ -563,31 +576,51 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
 #pragma unroll
   for (int i = 0; i < ZT; ++i) { zt[i] = s_z[i]; lt_[i] = s_lay[i]; }
 
+  int lay_mask = 0;
+#pragma unroll
+  for (int i = 0; i < ZT; ++i) if (i < nzt) lay_mask |= 1 << (lt_[i] - 1);
+
   for (int pi = warp; pi < np; pi += UNC_WARPS) {
     cplx accT[ZT], accA[ZT], accB[ZT];
 #pragma unroll
     for (int i = 0; i < ZT; ++i) { accT[i] = mk(0, 0); accA[i] = mk(0, 0); accB[i] = mk(0, 0); }
-    cplx f[ZT];
-    for (int i = 0; i < P.nts_pad / 32; ++i) {
-      const int idx = i * 32 + lane;
-      const double w = s_wj[idx];
-      if (idx < P.N) {
-        soln_literal<ZT>(P, T, pi, s_a2[idx], zt, lt_, nzt, f);
+    const cplx pp = T.p[pi], aux = T.aux[pi], aux2 = T.aux2[pi];
+    const int nts_rounds = P.nts_pad / 32;
+    // one abscissa per lane per round: tanh-sinh rounds first, then Gauss-Lobatto rounds
+    for (int i = 0; i < nts_rounds + rounds; ++i) {
+      const bool ts = i < nts_rounds;
+      const int idx = ts ? i * 32 + lane : P.nts_pad + (i - nts_rounds) * 32 + lane;
+      const bool valid = ts ? (idx < P.N) : (node0 + (i - nts_rounds) < nacc * G);
+      if (valid) {
+        const double w = s_wj[idx], a2v = s_a2[idx];
+        cplx f[ZT];
+        cplx eta;
+        Coef co[3];
+        if (ap_terms_fast(P, pp, aux, aux2, a2v, w, lay_mask, &eta, co)) {
 #pragma unroll
-        for (int k = 0; k < ZT; ++k) accT[k] = fma_acc(w, f[k], accT[k]);
-      }
-    }
-    for (int i = 0; i < rounds; ++i) {
-      const int idx = P.nts_pad + i * 32 + lane;
-      const double w = s_wj[idx];
-      if (node0 + i < nacc * G) {
-        soln_literal<ZT>(P, T, pi, s_a2[idx], zt, lt_, nzt, f);
-        if (i < iB) {
-#pragma unroll
-          for (int k = 0; k < ZT; ++k) accA[k] = fma_acc(w, f[k], accA[k]);
+          for (int k = 0; k < ZT; ++k)
+            if (k < nzt) {
+              const int L = lt_[k] - 1;
+              const Coef &c = (L == 0) ? co[0] : ((L == 1) ? co[1] : co[2]);
+              f[k] = eval_z_fast(eta, c, zt[k]);
+            } else f[k] = mk(0.0, 0.0);
         } else {
 #pragma unroll
-          for (int k = 0; k < ZT; ++k) accB[k] = fma_acc(w, f[k], accB[k]);
+          for (int k = 0; k < ZT; ++k)
+            if (k < nzt) {
+              cplx v = soln_literal_one(P, T, pi, a2v, zt[k], lt_[k]);
+              f[k] = mk(w * v.re, w * v.im);
+            } else f[k] = mk(0.0, 0.0);
+        }
+        if (ts) {
+#pragma unroll
+          for (int k = 0; k < ZT; ++k) accT[k] = caddf(accT[k], f[k]);
+        } else if (i - nts_rounds < iB) {
+#pragma unroll
+          for (int k = 0; k < ZT; ++k) accA[k] = caddf(accA[k], f[k]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < ZT; ++k) accB[k] = caddf(accB[k], f[k]);
         }
       }
     }
@@ -654,6 +687,212 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       else {
         J.s[o] = v;
         if (J.flags) J.flags[o] = s_flag[zi];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Grid kernel: lanes <-> z.  One CTA = one (t,r) column and a block of 32 z-values;
+// one warp per p.  The per-(a,p) terms (ap_terms_fast) are computed lane-parallel for 32
+// abscissae at a time and staged in shared memory; then every lane walks those 32
+// abscissae for ITS z (one exp_pm + one sincos each), accumulating the tanh-sinh sum
+// and the Gauss-Lobatto interval areas in abscissa order (the reference's own
+// summation order, driver.f90:135,201).  Abscissae whose Re(eta) exceeds the fast-path
+// bound take the literal path -- a warp-uniform branch in this layout.
+struct StageEnt {
+  cplx eta;
+  Coef co[3];
+};
+
+__host__ __device__ inline size_t grid_smem_bytes(int np, int na_seq) {
+  size_t b = 0;
+  b += (size_t)4 * np * sizeof(cplx);                       // p, lt, aux, aux2
+  b += (size_t)2 * na_seq * sizeof(double);                 // a2, wj
+  b += (size_t)np * 32 * sizeof(cplx);                      // totlap[p][lane]
+  size_t stage = (size_t)UNC_WARPS * 32 * sizeof(StageEnt) + (size_t)UNC_WARPS * 32 * sizeof(int);
+  size_t scratch = (size_t)UNC_WARPS * 3 * np * sizeof(cplx);  // de Hoog scratch aliases the stage
+  b += stage > scratch ? stage : scratch;
+  b += 64;
+  return (b + 15) & ~(size_t)15;
+}
+
+__global__ void __launch_bounds__(UNC_THREADS, 2)
+lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job J) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int np = P.np, nacc = P.nacc, G = P.G, N = P.N;
+  const int NA = N + nacc * G;
+  const int na_seq = (NA + 31) & ~31;
+  const int nzb = (J.nz + 31) / 32;
+  const long long col = blockIdx.x / nzb;
+  const int z0 = (int)(blockIdx.x % nzb) * 32;
+  const int nzv = min(32, J.nz - z0);
+
+  unsigned char *sp = smem_raw;
+  PTab T;
+  T.p = (cplx *)sp; sp += np * sizeof(cplx);
+  T.lt = (cplx *)sp; sp += np * sizeof(cplx);
+  T.aux = (cplx *)sp; sp += np * sizeof(cplx);
+  T.aux2 = (cplx *)sp; sp += np * sizeof(cplx);
+  double *s_a2 = (double *)sp; sp += na_seq * sizeof(double);
+  double *s_wj = (double *)sp; sp += na_seq * sizeof(double);
+  cplx *s_tot = (cplx *)sp; sp += (size_t)np * 32 * sizeof(cplx);
+  StageEnt *s_stage = (StageEnt *)sp;
+  int *s_ok = (int *)(sp + (size_t)UNC_WARPS * 32 * sizeof(StageEnt));
+  cplx *s_scr = (cplx *)sp;
+  {
+    size_t stage = (size_t)UNC_WARPS * 32 * sizeof(StageEnt) + (size_t)UNC_WARPS * 32 * sizeof(int);
+    size_t scratch = (size_t)UNC_WARPS * 3 * np * sizeof(cplx);
+    sp += stage > scratch ? stage : scratch;
+  }
+  int *s_misc = (int *)sp;  // [0] layer mask, [1..] unused
+
+  const double tD = J.tD[col / J.tdiv];
+  const int sv = J.sv[col / J.tdiv];
+  const double rD = J.rD[col % J.rmod];
+  const double tee = P.tee_mult * tD;
+  const double arg = P.j0z[sv - 1] / rD;                      // driver.f90:120
+  const double tscale = J.ts_scale ? J.ts_scale[col] : arg;  // driver.f90:121-126
+  const long long zbase = (J.zstride ? col * (long long)J.nz : 0) + z0;
+  const bool zvalid = lane < nzv;
+  const double myz = zvalid ? J.zD[zbase + lane] : 0.5;
+  const int mylay = zvalid ? J.zLay[zbase + lane] : 2;
+
+  // ---- prologue ---------------------------------------------------------------
+  if (tid == 0) s_misc[0] = 0;
+  for (int i = tid; i < np; i += UNC_THREADS) {
+    const double PI = 3.141592653589793;
+    double sigma = P.alpha - P.log_tol / (2.0 * tee);   // invlap.f90:166-170
+    cplx p = mk(sigma, PI * (double)i / tee);
+    T.p[i] = p;
+    T.lt[i] = laptime_dev(P, p);
+    cplx aux = mk(0.0, 0.0), aux2 = mk(0.0, 0.0);
+    if (P.model == 3) {
+      for (int m = 0; m < P.moench_M; ++m) aux = aux + 1.0 / (1.0 + p * (1.0 / P.moench_gamma[m]));
+    } else if (P.model == 2) {
+      cplx xi = P.rDw * csqrt_g(p);
+      cplx K[2];
+      cbesk01_dev(xi, K);
+      aux = 2.0 / (p * P.CDw * K[0] + xi * K[1]);
+      aux2 = p * P.tDb + 1.0;
+    }
+    T.aux[i] = aux;
+    T.aux2[i] = aux2;
+  }
+  for (int idx = tid; idx < na_seq; idx += UNC_THREADS) {
+    double a = 0.0, w = 0.0;
+    if (idx < N) {
+      a = (P.ts_T[idx] * tscale) / 2.0;  // integration.f90:62
+      w = P.ts_wc[idx] * (arg / 2.0);    // driver.f90:135,154 + Richardson (linear in tmp)
+    } else if (idx < NA) {
+      const int node = idx - N;
+      const int j = node / G, m = node - j * G;
+      const double lob = P.j0z[sv + j - 1] / rD;  // driver.f90:188-193
+      const double hib = P.j0z[sv + j] / rD;
+      const double width = hib - lob;
+      a = fma(width, P.gl_x[m], hib + lob) / 2.0;
+      w = P.gl_w[m] * (width / 2.0);
+    }
+    s_a2[idx] = a * a;
+    s_wj[idx] = (w != 0.0) ? w * (a * j0_dev(a * rD)) : 0.0;  // laplace_hankel_solutions.f90:118
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int m = zvalid ? (1 << (mylay - 1)) : 0;
+    for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+    if (lane == 0) s_misc[0] = m;
+  }
+  __syncthreads();
+  const int lay_mask = s_misc[0];
+  const int myL = mylay - 1;
+
+  // ---- phase A+B per p -----------------------------------------------------------
+  StageEnt *stage = s_stage + warp * 32;
+  int *okv = s_ok + warp * 32;
+  int stale = 0;
+  for (int pi = warp; pi < np; pi += UNC_WARPS) {
+    const cplx pp = T.p[pi], aux = T.aux[pi], aux2 = T.aux2[pi];
+    cplx series[UNC_MAX_NACC];
+    cplx acc = mk(0.0, 0.0), fin = mk(0.0, 0.0);
+    int seg = 0;  // 0: tanh-sinh, j>=1: Gauss-Lobatto interval j
+    for (int base = 0; base < NA; base += 32) {
+      {
+        const int idx = base + lane;
+        int ok = 0;
+        if (idx < NA) {
+          StageEnt e;
+          ok = ap_terms_fast(P, pp, aux, aux2, s_a2[idx], s_wj[idx], lay_mask, &e.eta, e.co) ? 1 : 0;
+          stage[lane] = e;
+        }
+        okv[lane] = ok;
+      }
+      __syncwarp();
+      const int cnt = min(32, NA - base);
+      for (int j = 0; j < cnt; ++j) {
+        const int id = base + j;
+        const int sg = (id < N) ? 0 : 1 + (id - N) / G;
+        if (sg != seg) {
+          if (seg == 0) fin = acc; else series[seg - 1] = acc;
+          acc = mk(0.0, 0.0);
+          seg = sg;
+        }
+        cplx f;
+        if (okv[j]) {
+          const StageEnt &e = stage[j];
+          f = eval_z_fast(e.eta, e.co[myL], myz);
+        } else {
+          cplx v = soln_literal_one(P, T, pi, s_a2[id], myz, mylay);
+          const double w = s_wj[id];
+          f = mk(w * v.re, w * v.im);
+        }
+        acc = caddf(acc, f);
+      }
+      __syncwarp();
+    }
+    if (seg == 0) fin = acc; else series[seg - 1] = acc;
+    // phase B: Wynn-epsilon (integration.f90:125-189), totlap (driver.f90:216)
+    {
+      const double nan = __longlong_as_double(0x7ff8000000000000LL);
+      const cplx lt = T.lt[pi];
+      bool any = false;
+      for (int j = 0; j < nacc; ++j) {
+        cplx a = series[j];
+        a = is_finite_c(a) ? a * lt : mk(nan, nan);
+        series[j] = a;
+        if (cabs_d(a) > 0.0) any = true;  // driver.f90:209
+      }
+      cplx infint = mk(0.0, 0.0);
+      if (any) infint = wynn_dev(series, nacc);
+      else stale = 1;
+      fin = is_finite_c(fin) ? fin * lt : mk(nan, nan);
+      s_tot[pi * 32 + lane] = fin + infint;
+    }
+  }
+  // per-z stale flag: OR over the warps via shared memory
+  __syncthreads();
+  int *s_flag = (int *)s_scr;  // stage no longer needed
+  if (tid < 32) s_flag[tid] = 0;
+  __syncthreads();
+  if (stale) atomicOr(&s_flag[lane], 1);
+  __syncthreads();
+  const int myflag = s_flag[lane];
+  __syncthreads();
+
+  // ---- phase C: de Hoog -------------------------------------------------------------
+  cplx *scr = s_scr + (size_t)warp * 3 * np;
+  for (int job = warp; job < 2 * nzv; job += UNC_WARPS) {
+    const int zi = job >> 1, deriv = job & 1;
+    double v = dehoog_warp(P, s_tot + zi, 32, deriv ? T.p : nullptr, tD, tee, scr, scr + np,
+                           scr + 2 * np, lane);
+    const int fl = __shfl_sync(0xffffffffu, myflag, zi);
+    if (lane == 0) {
+      const long long o = col * (long long)J.nz + z0 + zi;
+      if (deriv) J.ds[o] = v * tD;  // driver.f90:228
+      else {
+        J.s[o] = v;
+        if (J.flags) J.flags[o] = fl;
       }
     }
     __syncwarp();
