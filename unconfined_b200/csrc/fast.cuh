@@ -26,43 +26,113 @@ namespace unc {
 
 #define UNC_FAST_ETA_MAX 345.0  /* every intermediate of both formulations <= e^(2*345) < DBL_MAX */
 
-// exp(+-x), cosh x, sinh x from one range reduction: x = k ln2 + r, |r| <= ln2/2,
-// cosh r / sinh r by even/odd Taylor polynomials, exp(+-r) = cosh r +- sinh r.
+// Polynomial coefficients live in __constant__ memory so that DFMA takes them as
+// c[bank][offset] operands (ncu showed 35% of all issued instructions were UMOV/IMAD
+// constant materialisation when they were immediates).
+__constant__ double KEXP[16] = {
+    1.4426950408889634074,            // 0 log2(e)
+    6.93147180369123816490e-01,       // 1 ln2 hi
+    1.90821492927058770002e-10,       // 2 ln2 lo
+    6755399441055744.0,               // 3 1.5*2^52 (round-to-nearest-integer magic)
+    2.08767569878680989792e-09,       // 4 1/12!   cosh r = 1 + r2/2! + ... + r^12/12!
+    2.75573192239858906526e-07,       // 5 1/10!
+    2.48015873015873015873e-05,       // 6 1/8!
+    1.38888888888888888889e-03,       // 7 1/6!
+    4.16666666666666666667e-02,       // 8 1/4!
+    1.60590438368216145994e-10,       // 9 1/13!   sinh r = r (1 + r2/3! + ... + r^12/13!)
+    2.50521083854417187751e-08,       // 10 1/11!
+    2.75573192239858906526e-06,       // 11 1/9!
+    1.98412698412698412698e-04,       // 12 1/7!
+    8.33333333333333333333e-03,       // 13 1/5!
+    1.66666666666666666667e-01,       // 14 1/3!
+    0.0};
+// sin r = r + r^3 g(r^2), cos r = 1 - r^2/2 + r^4 h(r^2) on |r| <= pi/4
+// (tools/gen_sincos_poly.py: abs err 7e-17 / 1.2e-16)
+__constant__ double KTRIG[16] = {
+    6.36619772367581382433e-01,       // 0 2/pi
+    1.57079632679489655800e+00,       // 1 pi/2 hi
+    6.12323399573676603587e-17,       // 2 pi/2 lo
+    6755399441055744.0,               // 3 magic
+    -1.66666666666666657415e-01, 8.33333333333090113537e-03, -1.98412698366860079397e-04,   // 4.. g
+    2.75573160649867732950e-06, -2.50511240313820812782e-08, 1.59175674789067991500e-10,
+    4.16666666666666643537e-02, -1.38888888888873671991e-03, 2.48015872987202915510e-05,    // 10.. h
+    -2.75573172482293668695e-07, 2.08761413802949554280e-09, -1.13822809577026335532e-11};
+
+// exp(+-x) from one range reduction: x = k ln2 + r, |r| <= ln2/2, exp(+-r) = cosh r +- sinh r
+// (even/odd Taylor polynomials), scaled by 2^(+-k).  |x| <= ~700 on this path, so 2^k and
+// 2^-k are normal doubles.  *c_out/*s_out = cosh r, sinh r and *k_out = k for callers that
+// need cosh x / sinh x without cancellation.
+__device__ __forceinline__ void exp_pm_core(double x, double *ep, double *em, double *c_out,
+                                            double *s_out, int *k_out) {
+  const double km = fma(x, KEXP[0], KEXP[3]);
+  const int k = __double2loint(km);
+  const double kf = km - KEXP[3];
+  double r = fma(-kf, KEXP[1], x);
+  r = fma(-kf, KEXP[2], r);
+  const double r2 = r * r;
+  double c = fma(KEXP[4], r2, KEXP[5]);
+  c = fma(c, r2, KEXP[6]);
+  c = fma(c, r2, KEXP[7]);
+  c = fma(c, r2, KEXP[8]);
+  c = fma(c, r2, 0.5);
+  c = fma(c, r2, 1.0);
+  double s = fma(KEXP[9], r2, KEXP[10]);
+  s = fma(s, r2, KEXP[11]);
+  s = fma(s, r2, KEXP[12]);
+  s = fma(s, r2, KEXP[13]);
+  s = fma(s, r2, KEXP[14]);
+  s = fma(s * r2, r, r);
+  const double sp = __hiloint2double((1023 + k) << 20, 0);
+  const double sm = __hiloint2double((1023 - k) << 20, 0);
+  *ep = (c + s) * sp;
+  *em = (c - s) * sm;
+  *c_out = c;
+  *s_out = s;
+  *k_out = k;
+}
+
 struct rexp {
   double ep, em, ch, sh;
 };
 __device__ __forceinline__ rexp exp_pm(double x) {
-  const double L2E = 1.4426950408889634074, LN2H = 6.93147180369123816490e-01,
-               LN2L = 1.90821492927058770002e-10;
-  const double kf = rint(x * L2E);
-  double r = fma(-kf, LN2H, x);
-  r = fma(-kf, LN2L, r);
-  const double r2 = r * r;
-  double c = 2.08767569878680989792e-09;            // 1/12!
-  c = fma(c, r2, 2.75573192239858906526e-07);       // 1/10!
-  c = fma(c, r2, 2.48015873015873015873e-05);       // 1/8!
-  c = fma(c, r2, 1.38888888888888888889e-03);       // 1/6!
-  c = fma(c, r2, 4.16666666666666666667e-02);       // 1/4!
-  c = fma(c, r2, 0.5);
-  c = fma(c, r2, 1.0);
-  double s = 1.60590438368216145994e-10;            // 1/13!
-  s = fma(s, r2, 2.50521083854417187751e-08);       // 1/11!
-  s = fma(s, r2, 2.75573192239858906526e-06);       // 1/9!
-  s = fma(s, r2, 1.98412698412698412698e-04);       // 1/7!
-  s = fma(s, r2, 8.33333333333333333333e-03);       // 1/5!
-  s = fma(s, r2, 1.66666666666666666667e-01);       // 1/3!
-  s = fma(s * r2, r, r);
-  const int k = (int)kf;
-  // |k| <= 1020 on this path (|x| <= ~700): 2^k and 2^-k are normal doubles
-  const double sp = __longlong_as_double((long long)(1023 + k) << 52);
-  const double sm = __longlong_as_double((long long)(1023 - k) << 52);
   rexp o;
-  o.ep = (c + s) * sp;
-  o.em = (c - s) * sm;
+  double c, s;
+  int k;
+  exp_pm_core(x, &o.ep, &o.em, &c, &s, &k);
   // k == 0: the polynomials ARE cosh/sinh (no cancellation for small x)
   o.ch = (k == 0) ? c : 0.5 * (o.ep + o.em);
   o.sh = (k == 0) ? s : 0.5 * (o.ep - o.em);
   return o;
+}
+
+// sin and cos of y, |y| < ~2^20 (here |Im(eta) z| is at most a few thousand):
+// two-term Cody-Waite reduction by pi/2 (the FMA keeps k*pi/2_hi exact), kernel
+// polynomials, quadrant fix-up on the sign/high words.  <= ~1 ulp of 1 absolute.
+__device__ __forceinline__ void sincos_q(double y, double *sn, double *cs) {
+  const double km = fma(y, KTRIG[0], KTRIG[3]);
+  const int n = __double2loint(km);
+  const double kf = km - KTRIG[3];
+  double r = fma(-kf, KTRIG[1], y);
+  r = fma(-kf, KTRIG[2], r);
+  const double t = r * r;
+  double g = fma(KTRIG[9], t, KTRIG[8]);
+  g = fma(g, t, KTRIG[7]);
+  g = fma(g, t, KTRIG[6]);
+  g = fma(g, t, KTRIG[5]);
+  g = fma(g, t, KTRIG[4]);
+  const double s = fma(g * t, r, r);
+  double h = fma(KTRIG[15], t, KTRIG[14]);
+  h = fma(h, t, KTRIG[13]);
+  h = fma(h, t, KTRIG[12]);
+  h = fma(h, t, KTRIG[11]);
+  h = fma(h, t, KTRIG[10]);
+  const double c = fma(h * t, t, fma(t, -0.5, 1.0));
+  // quadrant n&3: sin = [s, c, -s, -c], cos = [c, -s, -c, s]
+  const bool sw = n & 1;
+  const double a = sw ? c : s, b = sw ? s : c;
+  const int sa = (n & 2) << 30, sb = ((n + 1) & 2) << 30;
+  *sn = __hiloint2double(__double2hiint(a) ^ sa, __double2loint(a));
+  *cs = __hiloint2double(__double2hiint(b) ^ sb, __double2loint(b));
 }
 
 // plain complex helpers for finite operands (no real->complex promotion)
@@ -85,7 +155,7 @@ struct cbundle {
 __device__ __forceinline__ cbundle cexp_bundle(double wr, double wi) {
   const rexp e = exp_pm(wr);
   double s, c;
-  sincos(wi, &s, &c);
+  sincos_q(wi, &s, &c);
   cbundle b;
   b.ep = mk(e.ep * c, e.ep * s);
   b.em = mk(e.em * c, -(e.em * s));
@@ -127,7 +197,7 @@ __device__ __forceinline__ bool ap_terms_fast(const DevParams &P, cplx p, cplx a
   }
   const cplx eta = csqrt_pos(cscalef(pa, 1.0 / P.kappa));
   *eta_out = eta;
-  if (!(eta.re <= UNC_FAST_ETA_MAX)) return false;
+  if (!(eta.re <= UNC_FAST_ETA_MAX && eta.im <= 2.0e5)) return false;  // sincos_q range
   const cbundle E1 = cexp_bundle(eta.re, eta.im);
   cplx K0;  // common prefactor of the layer functions, weight folded in
   if (model == 2) K0 = cscalef(cdivf(aux, cmulf(pa, aux2)), w / P.bD);            // uDf/bD :265-266,299
@@ -195,10 +265,11 @@ __device__ __forceinline__ bool ap_terms_fast(const DevParams &P, cplx p, cplx a
 
 // f(z) for one z given the per-(a,p) terms: one exp_pm + one sincos + 12 FMA
 __device__ __forceinline__ cplx eval_z_fast(cplx eta, const Coef &c, double z) {
-  const rexp e = exp_pm(eta.re * z);
-  double s, cs;
-  sincos(eta.im * z, &s, &cs);
-  const double pc = e.ep * cs, ps = e.ep * s, mc = e.em * cs, ms = e.em * s;
+  double ep, em, cc, ss, s, cs;
+  int kk;
+  exp_pm_core(eta.re * z, &ep, &em, &cc, &ss, &kk);
+  sincos_q(eta.im * z, &s, &cs);
+  const double pc = ep * cs, ps = ep * s, mc = em * cs, ms = em * s;
   // k0 + cp*(pc + i ps) + cm*(mc - i ms)
   double fr = fma(c.cp.re, pc, c.k0.re);
   fr = fma(-c.cp.im, ps, fr);

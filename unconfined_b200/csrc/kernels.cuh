@@ -816,11 +816,12 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
     const cplx pp = T.p[pi], aux = T.aux[pi], aux2 = T.aux2[pi];
     cplx series[UNC_MAX_NACC];
     cplx acc = mk(0.0, 0.0), fin = mk(0.0, 0.0);
-    int seg = 0;  // 0: tanh-sinh, j>=1: Gauss-Lobatto interval j
+    int seg = 0;        // 0: tanh-sinh, j>=1: Gauss-Lobatto interval j
+    int next_b = N;     // first abscissa index of the next segment
     for (int base = 0; base < NA; base += 32) {
+      int ok = 1;
       {
         const int idx = base + lane;
-        int ok = 0;
         if (idx < NA) {
           StageEnt e;
           ok = ap_terms_fast(P, pp, aux, aux2, s_a2[idx], s_wj[idx], lay_mask, &e.eta, e.co) ? 1 : 0;
@@ -828,26 +829,40 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
         }
         okv[lane] = ok;
       }
+      const bool all_ok = __all_sync(0xffffffffu, ok);
       __syncwarp();
       const int cnt = min(32, NA - base);
-      for (int j = 0; j < cnt; ++j) {
-        const int id = base + j;
-        const int sg = (id < N) ? 0 : 1 + (id - N) / G;
-        if (sg != seg) {
+      int j = 0;
+      while (j < cnt) {
+        const int jend = min(cnt, next_b - base);
+        if (all_ok) {
+          // hot loop: no branches, 4 broadcast LDS.128 + ~60 FP64 instructions per abscissa
+#pragma unroll 2
+          for (; j < jend; ++j) {
+            const cplx eta = stage[j].eta;
+            const Coef c = stage[j].co[myL];
+            acc = caddf(acc, eval_z_fast(eta, c, myz));
+          }
+        } else {
+          for (; j < jend; ++j) {
+            cplx f;
+            if (okv[j]) {
+              f = eval_z_fast(stage[j].eta, stage[j].co[myL], myz);
+            } else {
+              const int id = base + j;
+              cplx v = soln_literal_one(P, T, pi, s_a2[id], myz, mylay);
+              const double w = s_wj[id];
+              f = mk(w * v.re, w * v.im);
+            }
+            acc = caddf(acc, f);
+          }
+        }
+        if (base + j == next_b && next_b < NA) {
           if (seg == 0) fin = acc; else series[seg - 1] = acc;
           acc = mk(0.0, 0.0);
-          seg = sg;
+          seg += 1;
+          next_b += G;
         }
-        cplx f;
-        if (okv[j]) {
-          const StageEnt &e = stage[j];
-          f = eval_z_fast(e.eta, e.co[myL], myz);
-        } else {
-          cplx v = soln_literal_one(P, T, pi, s_a2[id], myz, mylay);
-          const double w = s_wj[id];
-          f = mk(w * v.re, w * v.im);
-        }
-        acc = caddf(acc, f);
       }
       __syncwarp();
     }
