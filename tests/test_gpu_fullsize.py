@@ -1,0 +1,82 @@
+"""Size-independent properties at BASELINE.json's full size: the 2^20-point C5a contour
+grid (Malama partial penetration) that bench.py times.  The oracle needs ~50 ms of CPU
+per point, so here it only checks a random sample; the rest are invariants."""
+import os
+
+import numpy as np
+import pytest
+
+import bench
+import unconfined_b200 as ub
+from oracle import oracle
+from helpers import check_parity, oracle_with_noise
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c5a():
+    os.environ.pop("UNC_FORCE_KERNEL", None)
+    d, t, r, z = bench.c5a_grid(0)
+    p, tD, sv, rD, zD, lay = bench.derive(d, t, r, z, ub)
+    prm = ub.Params(p)
+    s, ds, fl = ub.eval_grid(prm, tD, sv, rD, zD, lay, want_flags=True)
+    return dict(p=p, prm=prm, tD=tD, sv=sv, rD=rD, zD=zD, lay=lay, s=s, ds=ds, fl=fl)
+
+
+def test_full_grid_shape_determinism_and_finiteness(c5a):
+    g = c5a
+    assert g["s"].shape == (8, 1024, 128) and g["s"].size == 2 ** 20
+    s2, ds2 = ub.eval_grid(g["prm"], g["tD"], g["sv"], g["rD"], g["zD"], g["lay"])
+    assert np.array_equal(s2, g["s"], equal_nan=True) and np.array_equal(ds2, g["ds"], equal_nan=True)
+    clean = g["fl"] == 0
+    assert clean.mean() > 0.97
+    assert np.isfinite(g["s"][clean]).all()
+
+
+def test_full_grid_sharding_invariance(c5a):
+    g = c5a
+    half = 512
+    sa, da = ub.eval_grid(g["prm"], g["tD"], g["sv"], g["rD"][:half], g["zD"], g["lay"])
+    sb, db = ub.eval_grid(g["prm"], g["tD"], g["sv"], g["rD"][half:], g["zD"], g["lay"])
+    assert np.array_equal(np.concatenate([sa, sb], axis=1), g["s"], equal_nan=True)
+    assert np.array_equal(np.concatenate([da, db], axis=1), g["ds"], equal_nan=True)
+
+
+def test_full_grid_physics_monotone_in_time_and_radius(c5a):
+    g = c5a
+    s = g["s"][:, 64:, :]          # away from the overflow-affected smallest radii
+    scale = np.abs(s).max()
+    assert (np.diff(s, axis=0) > -1e-7 * scale).all()      # drawdown grows with time (step pumping)
+    late = g["s"][-1, 64:, 64]
+    assert (np.diff(late) < 1e-9 * scale).all()             # and decays with distance
+
+
+def test_full_grid_random_sample_against_oracle(c5a):
+    g = c5a
+    rng = np.random.default_rng(7)
+    n = 256
+    it, ir, iz = rng.integers(0, 8, n), rng.integers(0, 1024, n), rng.integers(0, 128, n)
+    args = (g["tD"][it], g["sv"][it], g["rD"][ir], g["zD"][iz], g["lay"][iz])
+    po = oracle.Params(g["p"])
+    so, do, sps, spd = oracle_with_noise(po, args, points=True, nsamples=2)
+    _, _, fo = oracle.eval_points(po, *args)
+    assert np.array_equal(fo, g["fl"][it, ir, iz])
+    keep = fo == 0
+    well = check_parity(g["s"][it, ir, iz][keep], g["ds"][it, ir, iz][keep], so[keep], do[keep],
+                        sps[keep], spd[keep], what="C5a sample")
+    assert well > 0.5     # most sampled points are well-conditioned and held to 1e-9 outright
+
+
+def test_grid_kernel_equals_point_kernel_on_sample(c5a):
+    g = c5a
+    rng = np.random.default_rng(11)
+    n = 4096
+    it, ir, iz = rng.integers(0, 8, n), rng.integers(64, 1024, n), rng.integers(0, 128, n)
+    sp_, dp_ = ub.eval_points(g["prm"], g["tD"][it], g["sv"][it], g["rD"][ir], g["zD"][iz], g["lay"][iz])
+    ref = g["s"][it, ir, iz]
+    rel = np.abs(sp_ - ref) / np.maximum(np.abs(ref), 1e-300)
+    # two different summation orders of the same arithmetic: agree far below the parity bar
+    # except where the result itself is rounding noise (tiny early-time drawdowns)
+    assert np.median(rel) < 1e-12
+    assert (rel < 1e-6).mean() > 0.98

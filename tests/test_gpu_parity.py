@@ -1,0 +1,181 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU
+oracle on the same inputs.  Tolerance: helpers.RTOL = 1e-9 relative (north_star) plus a
+multiple of the oracle's own libm-noise spread at ill-conditioned points (helpers.py)."""
+import os
+
+import numpy as np
+import pytest
+
+import unconfined_b200 as ub
+from oracle import oracle, deck
+from helpers import (load_deck, stale_scale, check_parity, oracle_with_noise, ROOT, RTOL)
+
+pytestmark = pytest.mark.gpu
+
+DECKS = ["theis-input.dat", "hantush-input.dat", "cape-cod-neuman74.in", "cape-cod-moench.in",
+         "malama-partpen-input.dat", "malama-fullpen-input.dat", "hantush-storage-input.dat",
+         "hantush-fullpen-test.in", "theis-contours-input.dat", "hantush-contours-input.dat"]
+
+
+@pytest.fixture(autouse=True)
+def _need_gpu():
+    assert ub.device_count() >= 1, "no CUDA device: the product path has no CPU fallback"
+    os.environ.pop("UNC_FORCE_KERNEL", None)
+    yield
+    os.environ.pop("UNC_FORCE_KERNEL", None)
+
+
+def run_deck(name, kernel=None, fresh=False):
+    d, pd = load_deck(name)
+    sc = None if fresh else stale_scale(d)
+    args = (d["tD"], d["sv"], d["rD"], d["zD"], d["zLay"])
+    so, do, sps, spd = oracle_with_noise(oracle.Params(pd), args, ts_scale=sc)
+    _, _, fo = oracle.eval_grid(oracle.Params(pd), *args, ts_scale=sc, carry=False)
+    if kernel:
+        os.environ["UNC_FORCE_KERNEL"] = kernel
+    sg, dg, fg = ub.eval_grid(ub.Params(pd), *args, ts_scale=sc, want_flags=True)
+    well = check_parity(sg, dg, so, do, sps, spd, what=f"{name}[{kernel or 'auto'}]")
+    assert np.array_equal(fo, fg), "stale-infint flags differ"
+    return sg, dg, so, do, well
+
+
+@pytest.mark.parametrize("name", DECKS)
+def test_deck_parity_reference_compatible(name):
+    run_deck(name)
+
+
+@pytest.mark.parametrize("name", ["hantush-input.dat", "cape-cod-neuman74.in", "cape-cod-moench.in",
+                                  "hantush-contours-input.dat", "theis-input.dat"])
+@pytest.mark.parametrize("kernel", ["point", "grid"])
+def test_both_kernels_each_deck(name, kernel):
+    run_deck(name, kernel=kernel)
+
+
+@pytest.mark.parametrize("name", ["theis-contours-input.dat", "hantush-contours-input.dat"])
+def test_contour_decks_fresh_abscissae(name):
+    run_deck(name, fresh=True)
+
+
+def test_baseline_configs_strict_1e9_on_drawdown():
+    """The four deck configs BASELINE.json names: dimensionless drawdown within 1e-9 outright."""
+    for name in ("theis-input.dat", "hantush-input.dat", "cape-cod-neuman74.in", "cape-cod-moench.in"):
+        sg, dg, so, do, well = run_deck(name)
+        rel = np.abs(sg - so) / np.abs(so)
+        assert rel.max() < RTOL, f"{name}: {rel.max()}"
+
+
+def test_against_committed_golden_fixtures():
+    for name in ("hantush-input.dat", "cape-cod-neuman74.in", "cape-cod-moench.in", "hantush-storage-input.dat"):
+        g = np.load(os.path.join(ROOT, "tests", "golden", "oracle_" + name.replace(".", "_") + ".npz"))
+        d, pd = load_deck(name)
+        sg, dg = ub.eval_grid(ub.Params(pd), g["tD"], g["sv"], g["rD"], g["zD"], g["zLay"],
+                              ts_scale=float(g["ts_scale"]))
+        assert np.max(np.abs(sg - g["s"]) / np.abs(g["s"])) < RTOL
+
+
+def test_non_finite_flow_matches():
+    """Overflowing integrands: Wynn truncation / sentinel / stale flags must agree."""
+    d, pd = load_deck("hantush-contours-input.dat")
+    rD = np.array([1e-3, 5e-3, 0.02, 0.075, 0.2])
+    args = (d["tD"], d["sv"], rD, d["zD"], d["zLay"])
+    so, do, fo = oracle.eval_grid(oracle.Params(pd), *args, carry=False)
+    for kernel in ("point", "grid"):
+        os.environ["UNC_FORCE_KERNEL"] = kernel
+        sg, dg, fg = ub.eval_grid(ub.Params(pd), *args, want_flags=True)
+        assert np.array_equal(fo, fg)
+        assert fo.any() and not fo.all()
+        assert np.array_equal(np.isnan(sg), np.isnan(so))
+        big = np.abs(so) > 1e5          # sentinel-dominated results (-999999.9 leaks through de Hoog)
+        fin = np.isfinite(so) & ~big
+        assert np.allclose(sg[fin], so[fin], rtol=1e-6, atol=1e-12)
+
+
+def scatter_inputs(n, seed=20261018):
+    d, pd = load_deck("malama-partpen-input.dat")
+    rng = np.random.default_rng(seed)
+    rD = 10 ** rng.uniform(-2, 1, n); zD = rng.uniform(0, 1, n); tD = 10 ** rng.uniform(-1, 7, n)
+    sv = oracle.split_index(tD, (2, 2))
+    lay = oracle.zlay(zD, d["lD"], d["dD"])
+    pd = dict(pd, j0z=oracle.j0_zeros(2 + pd["gl_nacc"] + 1))
+    return pd, (tD, sv, rD, zD, lay)
+
+
+def test_scattered_points_c5b_sample():
+    pd, args = scatter_inputs(192)
+    so, do, sps, spd = oracle_with_noise(oracle.Params(pd), args, points=True)
+    _, _, fo = oracle.eval_points(oracle.Params(pd), *args)
+    sg, dg, fg = ub.eval_points(ub.Params(pd), *args, want_flags=True)
+    assert np.array_equal(fo, fg)
+    keep = fo == 0                      # stale-infint points: documented deviation (flagged)
+    check_parity(sg[keep], dg[keep], so[keep], do[keep], sps[keep], spd[keep], what="scatter")
+
+
+@pytest.mark.parametrize("nz", [1, 2, 3, 5, 12, 33, 40])
+def test_ragged_z_counts_and_kernel_agreement(nz):
+    d, pd = load_deck("cape-cod-neuman74.in")
+    zD = np.linspace(0.0, 1.0, nz) if nz > 1 else np.array([0.4])
+    lay = oracle.zlay(zD, d["lD"], d["dD"])
+    tD, sv, rD = d["tD"][10:40:10], d["sv"][10:40:10], np.array([0.2, 0.5319, 3.0])
+    args = (tD, sv, rD, zD, lay)
+    so, do, sps, spd = oracle_with_noise(oracle.Params(pd), args, nsamples=2)
+    res = {}
+    for kernel in ("point", "grid"):
+        os.environ["UNC_FORCE_KERNEL"] = kernel
+        sg, dg = ub.eval_grid(ub.Params(pd), *args)
+        check_parity(sg, dg, so, do, sps, spd, what=f"nz={nz} {kernel}")
+        res[kernel] = sg
+
+
+def test_points_equal_grid_and_device_equals_host():
+    import torch
+    d, pd = load_deck("cape-cod-moench.in")
+    prm = ub.Params(pd)
+    tD, sv, rD, zD, lay = d["tD"][::9], d["sv"][::9], np.array([0.3, 0.6]), d["zD"], d["zLay"]
+    sg, dg = ub.eval_grid(prm, tD, sv, rD, zD, lay)
+    T, R, Z = np.meshgrid(np.arange(len(tD)), np.arange(len(rD)), np.arange(len(zD)), indexing="ij")
+    sp_, dp_ = ub.eval_points(prm, tD[T.ravel()], sv[T.ravel()], rD[R.ravel()], zD[Z.ravel()], lay[Z.ravel()])
+    assert np.allclose(sp_.reshape(sg.shape), sg, rtol=1e-10)
+    dev = torch.device("cuda", 0)
+    g = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dtype=dt)  # noqa: E731
+    ds_ = torch.empty(sg.size, dtype=torch.float64, device=dev); dd_ = torch.empty_like(ds_)
+    ub.eval_grid_device(prm, g(tD, torch.float64), g(sv, torch.int32), g(rD, torch.float64),
+                        g(zD, torch.float64), g(lay, torch.int32), ds_, dd_)
+    torch.cuda.synchronize()
+    assert np.array_equal(ds_.cpu().numpy().reshape(sg.shape), sg, equal_nan=True)
+    assert np.array_equal(dd_.cpu().numpy().reshape(sg.shape), dg, equal_nan=True)
+
+
+def test_time_behaviours_on_gpu():
+    d, pd = load_deck("hantush-input.dat")
+    args = (d["tD"][20:70:7], d["sv"][20:70:7], d["rD"], d["zD"], d["zLay"])
+    for tt, par in ((2, [0.0, 50.0]), (3, [0.5, 1.0]), (5, [10.0, 0.0]), (8, [10.0, 0.0]),
+                    (-2, [0.0, 20.0, 1e9, 1.0, 0.25])):
+        q = dict(pd, time_type=tt, time_par=par)
+        so, do, sps, spd = oracle_with_noise(oracle.Params(q), args, nsamples=2)
+        sg, dg = ub.eval_grid(ub.Params(q), *args)
+        check_parity(sg, dg, so, do, sps, spd, what=f"time_type {tt}")
+
+
+def test_storage_model_miller_branch():
+    """|rDw sqrt(p)| > 2 (very early time) exercises cbknu's Miller recurrence (cbessel.f90:5209-5327)."""
+    d, pd = load_deck("hantush-storage-input.dat")
+    tD = np.array([1e-9, 1e-8, 1e-6]); sv = np.array([1, 1, 1], np.int32)
+    args = (tD, sv, d["rD"], d["zD"], d["zLay"])
+    so, do, sps, spd = oracle_with_noise(oracle.Params(pd), args, nsamples=2)
+    sg, dg = ub.eval_grid(ub.Params(pd), *args)
+    check_parity(sg, dg, so, do, sps, spd, what="storage early time")
+
+
+def test_multi_gpu_sharding_is_invariant():
+    d, pd = load_deck("hantush-contours-input.dat")
+    prm = ub.Params(pd)
+    args = (d["tD"], d["sv"], d["rD"], d["zD"], d["zLay"])
+    s1, d1 = ub.eval_grid(prm, *args, ngpu=1)
+    n = ub.device_count()
+    s2, d2 = ub.eval_grid(prm, *args, ngpu=0)       # all visible GPUs
+    assert np.array_equal(s1, s2, equal_nan=True) and np.array_equal(d1, d2, equal_nan=True)
+    # column split across two calls == one call
+    sa, _ = ub.eval_grid(prm, d["tD"], d["sv"], d["rD"][:11], d["zD"], d["zLay"], ts_scale=None)
+    sb, _ = ub.eval_grid(prm, d["tD"], d["sv"], d["rD"][11:], d["zD"], d["zLay"], ts_scale=None)
+    assert np.array_equal(np.concatenate([sa, sb], axis=1), s1, equal_nan=True)
+    assert n >= 1
