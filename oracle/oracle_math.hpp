@@ -67,25 +67,39 @@ template <class T> struct cx {
 template <class T> inline cx<T> operator+(cx<T> a, cx<T> b) { return {a.re + b.re, a.im + b.im}; }
 template <class T> inline cx<T> operator-(cx<T> a, cx<T> b) { return {a.re - b.re, a.im - b.im}; }
 template <class T> inline cx<T> operator-(cx<T> a) { return {-a.re, -a.im}; }
+// Under jitter, complex products/quotients are also perturbed by ~half an ulp of their
+// MODULUS per component: an FMA-contracting build (gfortran -O3 -march=native, nvcc)
+// rounds a.re*b.re - a.im*b.im differently from this unfused code, and when the two
+// products nearly cancel that difference is large relative to the component itself.
+template <class T> inline cx<T> jit_mod(cx<T> r, double a, double b, unsigned salt) {
+  if (jitter().ulps == 0.0) return r;
+  T m = std::fabs(r.re) > std::fabs(r.im) ? std::fabs(r.re) : std::fabs(r.im);
+  if (!(m <= std::numeric_limits<T>::max())) return r;
+  const double e = 0.5 * jitter().ulps * 1.1102230246251565e-16;
+  return {r.re + (T)(jitter_u(a, b, salt) * e) * m, r.im + (T)(jitter_u(b, a, salt + 7) * e) * m};
+}
 // complex*complex, plain 4-multiply form (GCC tree-complex, Fortran rules)
 template <class T> inline cx<T> operator*(cx<T> a, cx<T> b) {
-  return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+  cx<T> r = {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+  return jit_mod(r, (double)r.re, (double)r.im, 60);
 }
 // complex/complex, GCC expand_complex_div_wide (Smith, no rescue)
 template <class T> inline cx<T> operator/(cx<T> a, cx<T> b) {
+  cx<T> r;
   if (std::fabs(b.re) < std::fabs(b.im)) {
     T ratio = b.re / b.im;
     T div = (b.re * ratio) + b.im;
     T tr = (a.re * ratio) + a.im;
     T ti = (a.im * ratio) - a.re;
-    return {tr / div, ti / div};
+    r = {tr / div, ti / div};
   } else {
     T ratio = b.im / b.re;
     T div = (b.im * ratio) + b.re;
     T tr = (a.im * ratio) + a.re;
     T ti = a.im - (a.re * ratio);
-    return {tr / div, ti / div};
+    r = {tr / div, ti / div};
   }
+  return jit_mod(r, (double)r.re, (double)r.im, 70);
 }
 // mixed real/complex: Fortran converts the real operand to complex first
 template <class T> inline cx<T> operator*(cx<T> a, T x) { return a * cx<T>(x, T(0)); }

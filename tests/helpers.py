@@ -44,9 +44,18 @@ def check_parity(got_s, got_ds, ref_s, ref_ds, sp_s, sp_ds, what=""):
     return float(well.mean())
 
 
-def oracle_with_noise(po, fn_args, points=False, nsamples=3, **kw):
+def oracle_with_noise(po, fn_args, points=False, nsamples=4, **kw):
+    """Oracle result plus its own rounding-noise envelope per point: the larger of
+    (a) the spread under <=2-ulp libm jitter (nsamples draws) and (b) the distance to the
+    same algorithm run in x87 long double.  The noise is heavy-tailed (Wynn's 1/denom, the
+    q-d divisions), hence both estimates and the factor NOISE_K."""
     if points:
-        f = lambda: oracle.eval_points(po, *fn_args, **kw)  # noqa: E731
+        f = lambda **k2: oracle.eval_points(po, *fn_args, **kw, **k2)  # noqa: E731
     else:
-        f = lambda: oracle.eval_grid(po, *fn_args, carry=False, **kw)  # noqa: E731
-    return oracle.noise_envelope(f, nsamples=nsamples)
+        f = lambda **k2: oracle.eval_grid(po, *fn_args, carry=False, **kw, **k2)  # noqa: E731
+    s0, d0, sp_s, sp_d = oracle.noise_envelope(f, nsamples=nsamples)
+    sl, dl = f(long_double=True)[:2]
+    with np.errstate(invalid="ignore"):
+        sp_s = np.fmax(sp_s, np.abs(s0 - sl))
+        sp_d = np.fmax(sp_d, np.abs(d0 - dl))
+    return s0, d0, sp_s, sp_d

@@ -1,0 +1,41 @@
+// TEST TOOL -- compiles the product's fast-path device math (unconfined_b200/csrc/fast.cuh)
+// for the HOST so that CPU tests can compare the algebra of ap_terms_fast/eval_z_fast
+// with the oracle at single (a,p,z) points.  Not linked into libunconfined_b200.so.
+#include <cstring>
+#include "../../unconfined_b200/csrc/fast.cuh"
+
+extern "C" {
+
+// f(z_i) = fp(a,p,z_i) of laplace_hankel_solutions.f90:30-116 without the common factor (:118).
+// Returns 0 if the fast path declined (Re eta beyond its bound), 1 otherwise.
+int hc_fast_soln(int model, double kappa, double alphaD, double beta, double lD, double dD, double bD,
+                 int moench_M, double aux_re, double aux_im, double aux2_re, double aux2_im, double a,
+                 double p_re, double p_im, int nz, const double *z, const int *lay, double *out,
+                 double *eta_out) {
+  unc::DevParams P;
+  std::memset(&P, 0, sizeof P);
+  P.model = model; P.kappa = kappa; P.alphaD = alphaD; P.beta = beta;
+  P.lD = lD; P.dD = dD; P.bD = bD; P.lD1 = 1.0 - lD; P.dD1 = 1.0 - dD; P.moench_M = moench_M;
+  int mask = 0;
+  for (int i = 0; i < nz; ++i) mask |= 1 << (lay[i] - 1);
+  unc::cplx eta;
+  unc::Coef co[3];
+  bool ok = unc::ap_terms_fast(P, unc::mk(p_re, p_im), unc::mk(aux_re, aux_im),
+                               unc::mk(aux2_re, aux2_im), a * a, 1.0, mask, &eta, co);
+  eta_out[0] = eta.re; eta_out[1] = eta.im;
+  if (!ok) return 0;
+  for (int i = 0; i < nz; ++i) {
+    unc::cplx f = unc::eval_z_fast(eta, co[lay[i] - 1], z[i]);
+    out[2 * i] = f.re; out[2 * i + 1] = f.im;
+  }
+  return 1;
+}
+
+void hc_exp_pm(double x, double *out) {
+  unc::rexp e = unc::exp_pm(x);
+  out[0] = e.ep; out[1] = e.em; out[2] = e.ch; out[3] = e.sh;
+}
+
+void hc_sincos(double y, double *out) { unc::sincos_q(y, &out[0], &out[1]); }
+
+}  // extern "C"

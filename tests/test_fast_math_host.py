@@ -1,0 +1,160 @@
+"""CPU tests of the PRODUCT's fast-path algebra (csrc/fast.cuh compiled for the host by
+tests/hostcheck) against the oracle's literal restatement evaluated in long double at
+single (a,p,z) points, for every model and layer.  This pins the closed forms used on the
+GPU (classical Hantush layer functions, folded water-table term) to the reference formulas."""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import mpmath as mp
+import numpy as np
+import pytest
+
+from oracle import oracle
+from helpers import load_deck, ROOT
+
+HC_DIR = os.path.join(ROOT, "tests", "hostcheck")
+
+
+@pytest.fixture(scope="module")
+def hc():
+    so = os.path.join(HC_DIR, "libhostcheck.so")
+    src = os.path.join(HC_DIR, "hostcheck.cu")
+    dep = os.path.join(ROOT, "unconfined_b200", "csrc", "fast.cuh")
+    if not os.path.exists(so) or max(os.path.getmtime(src), os.path.getmtime(dep)) > os.path.getmtime(so):
+        subprocess.run(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
+                        "-Xcompiler", "-fPIC", "-shared", "-o", so, src], check=True, capture_output=True)
+    return C.CDLL(so)
+
+
+def test_exp_pm_and_sincos_accuracy(hc):
+    mp.mp.dps = 40
+    out = (C.c_double * 4)()
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for x in np.concatenate([rng.uniform(-700, 700, 400), rng.uniform(-1, 1, 200), [0.0, 1e-9, -1e-5, 0.3465, -0.3467]]):
+        hc.hc_exp_pm(C.c_double(x), out)
+        ex = [mp.exp(x), mp.exp(-x), mp.cosh(x), mp.sinh(x)]
+        for got, want in zip(out, ex):
+            err = abs(mp.mpf(got) - want) / (abs(want) if want != 0 else 1)
+            worst = max(worst, float(err))
+    assert worst < 4.5e-16, worst                      # <= 2 ulp, sinh accurate for small x
+    o2 = (C.c_double * 2)()
+    worst = 0.0
+    for y in np.concatenate([rng.uniform(-3000, 3000, 600), rng.uniform(-1, 1, 100), [0.0, math.pi / 2, 1e5, -1.9e5]]):
+        hc.hc_sincos(C.c_double(y), o2)
+        worst = max(worst, abs(o2[0] - float(mp.sin(mp.mpf(float(y))))), abs(o2[1] - float(mp.cos(mp.mpf(float(y))))))
+    assert worst < 2.3e-16, worst                      # absolute (amplitude 1)
+
+
+def fast_soln(hc, pd, a, p, zD, lay, aux=0j, aux2=0j):
+    n = len(zD)
+    z = (C.c_double * n)(*zD); l = (C.c_int * n)(*[int(x) for x in lay])
+    out = (C.c_double * (2 * n))(); eta = (C.c_double * 2)()
+    ok = hc.hc_fast_soln(int(pd["model"]), C.c_double(pd["kappa"]), C.c_double(pd["alphaD"]),
+                         C.c_double(pd["beta"]), C.c_double(pd["lD"]), C.c_double(pd["dD"]),
+                         C.c_double(pd["bD"]), len(pd.get("moench_gamma", [])), C.c_double(aux.real),
+                         C.c_double(aux.imag), C.c_double(aux2.real), C.c_double(aux2.imag),
+                         C.c_double(a), C.c_double(p.real), C.c_double(p.imag), n, z, l, out, eta)
+    return ok, np.array(out[:]).view(np.complex128), complex(eta[0], eta[1])
+
+
+CASES = [("hantush-input.dat", 1), ("cape-cod-neuman74.in", 5), ("cape-cod-moench.in", 3),
+         ("malama-fullpen-input.dat", 4), ("theis-input.dat", 0), ("malama-partpen-input.dat", 5)]
+
+
+def literal_truth(pd, a, p, z, L):
+    """laplace_hankel_solutions.f90:30-116 exactly as written, in 40-digit arithmetic."""
+    model = pd["model"]
+    p = mp.mpc(p.real, p.imag)
+    th = 2 / (p + a * a)
+    if model == 0:
+        return complex(th)
+    eta = mp.sqrt((p + a * a) / pd["kappa"])
+    dD1, lD1 = 1 - mp.mpf(pd["dD"]), 1 - mp.mpf(pd["lD"])
+
+    def udp(z, L):
+        ff1, ff2, sh = mp.sinh(eta * pd["dD"]), mp.sinh(eta * lD1), mp.sinh(eta)
+        g2 = (ff1 * mp.cosh(eta * z) + ff2 * mp.cosh(eta * (1 - z))) / sh
+        if L == 1:
+            u = (mp.exp(-eta * lD1) - (ff1 + mp.exp(-eta) * ff2) / sh) * mp.cosh(eta * z)
+        elif L == 2:
+            u = 1 - g2
+        else:
+            u = mp.cosh(eta * (dD1 - z)) - g2
+        return u * th / pd["bD"]
+    if model == 1:
+        return complex(udp(z, L))
+    xi = eta * pd["alphaD"] / p
+    if model == 3:
+        xi = xi * len(pd["moench_gamma"]) / sum(1 / (1 + p / g) for g in pd["moench_gamma"])
+    u = th if model == 4 else udp(z, L)
+    top = th if model == 4 else udp(mp.mpf(1), 3)
+    if eta.real < mp.mpf("12.014551129705717"):
+        f = u - top * mp.cosh(eta * z) / ((1 + pd["beta"] * eta * xi) * mp.cosh(eta) + xi * mp.sinh(eta))
+    else:
+        f = u - top * mp.exp(eta * (z - 1)) / (1 + pd["beta"] * eta * xi + xi)
+    return complex(f)
+
+
+@pytest.mark.parametrize("name,model", CASES)
+def test_fast_path_matches_literal_formulas(hc, name, model):
+    mp.mp.dps = 40
+    d, pd = load_deck(name)
+    assert pd["model"] == model
+    po = oracle.Params(pd)
+    zD = np.array([0.0, 0.1, 0.5 * (1 - pd["lD"]), 1 - pd["lD"] + 0.3 * pd["bD"], 1 - pd["lD"] + 0.9 * pd["bD"],
+                   1 - 0.5 * pd["dD"], 1.0])
+    lay = oracle.zlay(zD, pd["lD"], pd["dD"])
+    worst = 0.0
+    for tD in (0.05, 3.0, 1e3, 1e7):
+        pv = oracle.pvalues(po, 2 * tD)
+        for a in (1e-4, 0.03, 0.7, 5.0, 40.0, 150.0):
+            for k in (0, 1, len(pv) // 2, len(pv) - 1):
+                aux = 0j
+                if model == 3:
+                    aux = sum(1 / (1 + pv[k] / g) for g in pd["moench_gamma"])
+                ok, got, eta = fast_soln(hc, pd, a, complex(pv[k]), zD, lay, aux)
+                if not ok:
+                    assert eta.real > 345.0
+                    continue
+                scale = abs(2 / (pv[k] + a * a)) / (1.0 if model in (0, 4) else pd["bD"])
+                for i in range(len(zD)):
+                    tr = literal_truth(pd, a, complex(pv[k]), mp.mpf(float(zD[i])), int(lay[i]))
+                    # relative to the natural scale of the kernel (|theis|/bD) or to the value
+                    # itself where a layer formula is used outside its range (zD=1 is
+                    # classified "beside the screen" by driver_io.f90:579-581 and blows up)
+                    worst = max(worst, abs(got[i] - tr) / max(scale, abs(tr)))
+    assert worst < 2e-13, worst
+
+
+def test_fast_path_is_closer_to_long_double_truth_than_the_double_literal(hc):
+    """Where the reference's expressions cancel (above the screen, large eta) the closed form
+    keeps its digits: compare both against the long-double evaluation of the literal formulas."""
+    d, pd = load_deck("hantush-input.dat")
+    pq = dict(pd, time_type=3, time_par=[0.0, 1.0])
+    po = oracle.Params(pq)
+    zD = np.array([0.97, 0.99]); lay = oracle.zlay(zD, pd["lD"], pd["dD"])
+    assert lay.tolist() == [3, 3]
+    tD, a = 1.0, 60.0
+    pv = oracle.pvalues(po, 2 * tD)
+    ref_d = oracle.soln(po, a, 0.0, tD, zD, lay) / a
+    # long double literal via eval of the same routine is not exposed per point; use mpmath
+    mp.mp.dps = 40
+    k = 3
+    p = mp.mpc(pv[k].real, pv[k].imag)
+    eta = mp.sqrt((p + a * a) / pd["kappa"])
+    dD1, lD1 = 1 - mp.mpf(pd["dD"]), 1 - mp.mpf(pd["lD"])
+    truth = []
+    for z in zD:
+        g1 = mp.cosh(eta * (dD1 - z))
+        g2 = (mp.sinh(eta * pd["dD"]) * mp.cosh(eta * z) + mp.sinh(eta * lD1) * mp.cosh(eta * (1 - z))) / mp.sinh(eta)
+        truth.append(complex((g1 - g2) * 2 / (p + a * a) / pd["bD"]))
+    truth = np.array(truth)
+    ok, got, _ = fast_soln(hc, pd, a, complex(pv[k]), zD, lay)
+    assert ok
+    e_fast = np.abs(got - truth) / np.abs(truth)
+    e_lit = np.abs(ref_d[k] - truth) / np.abs(truth)
+    assert e_fast.max() < 1e-12
+    assert e_fast.max() <= e_lit.max() * 1.01 + 1e-15

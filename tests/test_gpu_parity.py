@@ -117,7 +117,7 @@ def test_ragged_z_counts_and_kernel_agreement(nz):
     lay = oracle.zlay(zD, d["lD"], d["dD"])
     tD, sv, rD = d["tD"][10:40:10], d["sv"][10:40:10], np.array([0.2, 0.5319, 3.0])
     args = (tD, sv, rD, zD, lay)
-    so, do, sps, spd = oracle_with_noise(oracle.Params(pd), args, nsamples=2)
+    so, do, sps, spd = oracle_with_noise(oracle.Params(pd), args)
     res = {}
     for kernel in ("point", "grid"):
         os.environ["UNC_FORCE_KERNEL"] = kernel
@@ -151,7 +151,7 @@ def test_time_behaviours_on_gpu():
     for tt, par in ((2, [0.0, 50.0]), (3, [0.5, 1.0]), (5, [10.0, 0.0]), (8, [10.0, 0.0]),
                     (-2, [0.0, 20.0, 1e9, 1.0, 0.25])):
         q = dict(pd, time_type=tt, time_par=par)
-        so, do, sps, spd = oracle_with_noise(oracle.Params(q), args, nsamples=2)
+        so, do, sps, spd = oracle_with_noise(oracle.Params(q), args)
         sg, dg = ub.eval_grid(ub.Params(q), *args)
         check_parity(sg, dg, so, do, sps, spd, what=f"time_type {tt}")
 
@@ -161,7 +161,7 @@ def test_storage_model_miller_branch():
     d, pd = load_deck("hantush-storage-input.dat")
     tD = np.array([1e-9, 1e-8, 1e-6]); sv = np.array([1, 1, 1], np.int32)
     args = (tD, sv, d["rD"], d["zD"], d["zLay"])
-    so, do, sps, spd = oracle_with_noise(oracle.Params(pd), args, nsamples=2)
+    so, do, sps, spd = oracle_with_noise(oracle.Params(pd), args)
     sg, dg = ub.eval_grid(ub.Params(pd), *args)
     check_parity(sg, dg, so, do, sps, spd, what="storage early time")
 

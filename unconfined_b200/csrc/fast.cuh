@@ -20,7 +20,9 @@
 // beyond that the caller uses the literal path, which overflows exactly where the
 // reference does.
 #pragma once
+#include "params.cuh"
 #include "cmath.cuh"
+#include <cstring>
 
 namespace unc {
 
@@ -29,43 +31,71 @@ namespace unc {
 // Polynomial coefficients live in __constant__ memory so that DFMA takes them as
 // c[bank][offset] operands (ncu showed 35% of all issued instructions were UMOV/IMAD
 // constant materialisation when they were immediates).
-__constant__ double KEXP[16] = {
-    1.4426950408889634074,            // 0 log2(e)
-    6.93147180369123816490e-01,       // 1 ln2 hi
-    1.90821492927058770002e-10,       // 2 ln2 lo
-    6755399441055744.0,               // 3 1.5*2^52 (round-to-nearest-integer magic)
-    2.08767569878680989792e-09,       // 4 1/12!   cosh r = 1 + r2/2! + ... + r^12/12!
-    2.75573192239858906526e-07,       // 5 1/10!
-    2.48015873015873015873e-05,       // 6 1/8!
-    1.38888888888888888889e-03,       // 7 1/6!
-    4.16666666666666666667e-02,       // 8 1/4!
-    1.60590438368216145994e-10,       // 9 1/13!   sinh r = r (1 + r2/3! + ... + r^12/13!)
-    2.50521083854417187751e-08,       // 10 1/11!
-    2.75573192239858906526e-06,       // 11 1/9!
-    1.98412698412698412698e-04,       // 12 1/7!
-    8.33333333333333333333e-03,       // 13 1/5!
-    1.66666666666666666667e-01,       // 14 1/3!
-    0.0};
+#define UNC_KEXP_INIT { \
+    1.4426950408889634074,             \
+    6.93147180369123816490e-01,        \
+    1.90821492927058770002e-10,        \
+    6755399441055744.0,                \
+    2.08767569878680989792e-09,        \
+    2.75573192239858906526e-07,        \
+    2.48015873015873015873e-05,        \
+    1.38888888888888888889e-03,        \
+    4.16666666666666666667e-02,        \
+    1.60590438368216145994e-10,        \
+    2.50521083854417187751e-08,        \
+    2.75573192239858906526e-06,        \
+    1.98412698412698412698e-04,        \
+    8.33333333333333333333e-03,        \
+    1.66666666666666666667e-01,        \
+    0.0}
+__constant__ double KEXP_D[16] = UNC_KEXP_INIT;
+static const double KEXP_H[16] = UNC_KEXP_INIT;
+
 // sin r = r + r^3 g(r^2), cos r = 1 - r^2/2 + r^4 h(r^2) on |r| <= pi/4
 // (tools/gen_sincos_poly.py: abs err 7e-17 / 1.2e-16)
-__constant__ double KTRIG[16] = {
-    6.36619772367581382433e-01,       // 0 2/pi
-    1.57079632679489655800e+00,       // 1 pi/2 hi
-    6.12323399573676603587e-17,       // 2 pi/2 lo
-    6755399441055744.0,               // 3 magic
-    -1.66666666666666657415e-01, 8.33333333333090113537e-03, -1.98412698366860079397e-04,   // 4.. g
-    2.75573160649867732950e-06, -2.50511240313820812782e-08, 1.59175674789067991500e-10,
-    4.16666666666666643537e-02, -1.38888888888873671991e-03, 2.48015872987202915510e-05,    // 10.. h
-    -2.75573172482293668695e-07, 2.08761413802949554280e-09, -1.13822809577026335532e-11};
+#define UNC_KTRIG_INIT { \
+    6.36619772367581382433e-01,        \
+    1.57079632679489655800e+00,        \
+    6.12323399573676603587e-17,        \
+    6755399441055744.0,                \
+    -1.66666666666666657415e-01, 8.33333333333090113537e-03, -1.98412698366860079397e-04,    \
+    2.75573160649867732950e-06, -2.50511240313820812782e-08, 1.59175674789067991500e-10, \
+    4.16666666666666643537e-02, -1.38888888888873671991e-03, 2.48015872987202915510e-05,     \
+    -2.75573172482293668695e-07, 2.08761413802949554280e-09, -1.13822809577026335532e-11}
+__constant__ double KTRIG_D[16] = UNC_KTRIG_INIT;
+static const double KTRIG_H[16] = UNC_KTRIG_INIT;
+
+
+#ifdef __CUDA_ARCH__
+#define KEXP KEXP_D
+#define KTRIG KTRIG_D
+#define UNC_LOINT(x) __double2loint(x)
+#define UNC_HIINT(x) __double2hiint(x)
+#define UNC_HILO2D(h, l) __hiloint2double(h, l)
+#else
+// host mirrors: the same functions compile for the CPU so that tests/ can check the
+// fast-path algebra against the oracle without a GPU (tests/hostcheck); never used by
+// the product, whose entry points only launch kernels.
+#define KEXP KEXP_H
+#define KTRIG KTRIG_H
+static inline int unc_loint_h(double x) { long long b; std::memcpy(&b, &x, 8); return (int)(b & 0xffffffffLL); }
+static inline int unc_hiint_h(double x) { long long b; std::memcpy(&b, &x, 8); return (int)(b >> 32); }
+static inline double unc_hilo2d_h(int h, int l) {
+  long long b = ((long long)h << 32) | (unsigned int)l; double x; std::memcpy(&x, &b, 8); return x;
+}
+#define UNC_LOINT(x) unc_loint_h(x)
+#define UNC_HIINT(x) unc_hiint_h(x)
+#define UNC_HILO2D(h, l) unc_hilo2d_h(h, l)
+#endif
 
 // exp(+-x) from one range reduction: x = k ln2 + r, |r| <= ln2/2, exp(+-r) = cosh r +- sinh r
 // (even/odd Taylor polynomials), scaled by 2^(+-k).  |x| <= ~700 on this path, so 2^k and
 // 2^-k are normal doubles.  *c_out/*s_out = cosh r, sinh r and *k_out = k for callers that
 // need cosh x / sinh x without cancellation.
-__device__ __forceinline__ void exp_pm_core(double x, double *ep, double *em, double *c_out,
+__host__ __device__ __forceinline__ void exp_pm_core(double x, double *ep, double *em, double *c_out,
                                             double *s_out, int *k_out) {
   const double km = fma(x, KEXP[0], KEXP[3]);
-  const int k = __double2loint(km);
+  const int k = UNC_LOINT(km);
   const double kf = km - KEXP[3];
   double r = fma(-kf, KEXP[1], x);
   r = fma(-kf, KEXP[2], r);
@@ -82,8 +112,8 @@ __device__ __forceinline__ void exp_pm_core(double x, double *ep, double *em, do
   s = fma(s, r2, KEXP[13]);
   s = fma(s, r2, KEXP[14]);
   s = fma(s * r2, r, r);
-  const double sp = __hiloint2double((1023 + k) << 20, 0);
-  const double sm = __hiloint2double((1023 - k) << 20, 0);
+  const double sp = UNC_HILO2D((1023 + k) << 20, 0);
+  const double sm = UNC_HILO2D((1023 - k) << 20, 0);
   *ep = (c + s) * sp;
   *em = (c - s) * sm;
   *c_out = c;
@@ -94,7 +124,7 @@ __device__ __forceinline__ void exp_pm_core(double x, double *ep, double *em, do
 struct rexp {
   double ep, em, ch, sh;
 };
-__device__ __forceinline__ rexp exp_pm(double x) {
+__host__ __device__ __forceinline__ rexp exp_pm(double x) {
   rexp o;
   double c, s;
   int k;
@@ -108,9 +138,9 @@ __device__ __forceinline__ rexp exp_pm(double x) {
 // sin and cos of y, |y| < ~2^20 (here |Im(eta) z| is at most a few thousand):
 // two-term Cody-Waite reduction by pi/2 (the FMA keeps k*pi/2_hi exact), kernel
 // polynomials, quadrant fix-up on the sign/high words.  <= ~1 ulp of 1 absolute.
-__device__ __forceinline__ void sincos_q(double y, double *sn, double *cs) {
+__host__ __device__ __forceinline__ void sincos_q(double y, double *sn, double *cs) {
   const double km = fma(y, KTRIG[0], KTRIG[3]);
-  const int n = __double2loint(km);
+  const int n = UNC_LOINT(km);
   const double kf = km - KTRIG[3];
   double r = fma(-kf, KTRIG[1], y);
   r = fma(-kf, KTRIG[2], r);
@@ -131,28 +161,28 @@ __device__ __forceinline__ void sincos_q(double y, double *sn, double *cs) {
   const bool sw = n & 1;
   const double a = sw ? c : s, b = sw ? s : c;
   const int sa = (n & 2) << 30, sb = ((n + 1) & 2) << 30;
-  *sn = __hiloint2double(__double2hiint(a) ^ sa, __double2loint(a));
-  *cs = __hiloint2double(__double2hiint(b) ^ sb, __double2loint(b));
+  *sn = UNC_HILO2D(UNC_HIINT(a) ^ sa, UNC_LOINT(a));
+  *cs = UNC_HILO2D(UNC_HIINT(b) ^ sb, UNC_LOINT(b));
 }
 
 // plain complex helpers for finite operands (no real->complex promotion)
-__device__ __forceinline__ cplx cmulf(cplx a, cplx b) {
+__host__ __device__ __forceinline__ cplx cmulf(cplx a, cplx b) {
   return mk(fma(a.re, b.re, -(a.im * b.im)), fma(a.re, b.im, a.im * b.re));
 }
-__device__ __forceinline__ cplx crecipf(cplx b) {
+__host__ __device__ __forceinline__ cplx crecipf(cplx b) {
   const double d = 1.0 / fma(b.re, b.re, b.im * b.im);
   return mk(b.re * d, -(b.im * d));
 }
-__device__ __forceinline__ cplx cdivf(cplx a, cplx b) { return cmulf(a, crecipf(b)); }
-__device__ __forceinline__ cplx caddf(cplx a, cplx b) { return mk(a.re + b.re, a.im + b.im); }
-__device__ __forceinline__ cplx csubf(cplx a, cplx b) { return mk(a.re - b.re, a.im - b.im); }
-__device__ __forceinline__ cplx cscalef(cplx a, double x) { return mk(a.re * x, a.im * x); }
+__host__ __device__ __forceinline__ cplx cdivf(cplx a, cplx b) { return cmulf(a, crecipf(b)); }
+__host__ __device__ __forceinline__ cplx caddf(cplx a, cplx b) { return mk(a.re + b.re, a.im + b.im); }
+__host__ __device__ __forceinline__ cplx csubf(cplx a, cplx b) { return mk(a.re - b.re, a.im - b.im); }
+__host__ __device__ __forceinline__ cplx cscalef(cplx a, double x) { return mk(a.re * x, a.im * x); }
 
 // complex exp(+-w), cosh w, sinh w of w = eta*c
 struct cbundle {
   cplx ep, em, ch, sh;
 };
-__device__ __forceinline__ cbundle cexp_bundle(double wr, double wi) {
+__host__ __device__ __forceinline__ cbundle cexp_bundle(double wr, double wi) {
   const rexp e = exp_pm(wr);
   double s, c;
   sincos_q(wi, &s, &c);
@@ -165,7 +195,7 @@ __device__ __forceinline__ cbundle cexp_bundle(double wr, double wi) {
 }
 
 // sqrt of z with Re z > 0 (eta = sqrt((p+a^2)/kappa)), glibc's formula for that branch
-__device__ __forceinline__ cplx csqrt_pos(cplx z) {
+__host__ __device__ __forceinline__ cplx csqrt_pos(cplx z) {
   if (z.im == 0.0) return mk(sqrt(z.re), 0.0);
   const double d = sqrt(fma(z.re, z.re, z.im * z.im));
   const double r = sqrt(0.5 * (d + z.re));
@@ -182,7 +212,7 @@ struct Coef {  // f(z) = k0 + cp*exp(eta z) + cm*exp(-eta z)
 // times a*J0(a rD)) is folded into the coefficients.
 //   aux  : model 3: sum_m 1/(1+p/gamma_m);  model 2: A0(p) = 2/(p CDw K0 + xi K1)
 //   aux2 : model 2: p*tDb + 1
-__device__ __forceinline__ bool ap_terms_fast(const DevParams &P, cplx p, cplx aux, cplx aux2,
+__host__ __device__ __forceinline__ bool ap_terms_fast(const DevParams &P, cplx p, cplx aux, cplx aux2,
                                               double a2, double w, int lay_mask, cplx *eta_out,
                                               Coef *co /* [3], indexed by layer-1 */) {
   const int model = P.model;
@@ -264,7 +294,7 @@ __device__ __forceinline__ bool ap_terms_fast(const DevParams &P, cplx p, cplx a
 }
 
 // f(z) for one z given the per-(a,p) terms: one exp_pm + one sincos + 12 FMA
-__device__ __forceinline__ cplx eval_z_fast(cplx eta, const Coef &c, double z) {
+__host__ __device__ __forceinline__ cplx eval_z_fast(cplx eta, const Coef &c, double z) {
   double ep, em, cc, ss, s, cs;
   int kk;
   exp_pm_core(eta.re * z, &ep, &em, &cc, &ss, &kk);
