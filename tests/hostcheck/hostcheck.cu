@@ -21,7 +21,8 @@ int hc_fast_soln(int model, double kappa, double alphaD, double beta, double lD,
   unc::cplx eta;
   unc::Coef co[3];
   bool ok = unc::ap_terms_fast(P, unc::mk(p_re, p_im), unc::mk(aux_re, aux_im),
-                               unc::mk(aux2_re, aux2_im), a * a, 1.0, mask, &eta, co);
+                               unc::mk(aux2_re, aux2_im), a * a, 1.0, mask,
+                               unc::fast_eta_max(P, mask, 1.0), &eta, co);
   eta_out[0] = eta.re; eta_out[1] = eta.im;
   if (!ok) return 0;
   for (int i = 0; i < nz; ++i) {

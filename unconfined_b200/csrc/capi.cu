@@ -307,22 +307,30 @@ int launch_zt(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t 
   return UNC_OK;
 }
 
-int launch_grid(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
+template <int ZL>
+int launch_grid_zl(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
   const int NA = P.N + P.nacc * P.G;
-  const size_t smem = unc::grid_smem_bytes(P.np, (NA + 31) & ~31);
+  const size_t smem = unc::grid_smem_bytes(P.np, (NA + 31) & ~31, ZL);
   if (smem > 227 * 1024) return fail(UNC_ERR_UNSUPPORTED, "shared memory need %zu B exceeds 227 KB", smem);
   DevCtx &c = g_ctx[dev];
-  if (!c.smem_set[8]) {
-    CK(cudaFuncSetAttribute(unc::lh_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    c.smem_set[8] = true;
+  if (!c.smem_set[6 + ZL]) {
+    CK(cudaFuncSetAttribute(unc::lh_grid_kernel<ZL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    c.smem_set[6 + ZL] = true;
   }
-  const long long nblk = J.ncol * ((J.nz + 31) / 32);
+  const long long nblk = J.ncol * ((J.nz + 32 * ZL - 1) / (32 * ZL));
   if (nblk <= 0) return UNC_OK;
   if (nblk > 2147483647LL) return fail(UNC_ERR_UNSUPPORTED, "too many work items (%lld)", nblk);
-  unc::lh_grid_kernel<<<(unsigned)nblk, UNC_THREADS, smem, st>>>(P, J);
+  unc::lh_grid_kernel<ZL><<<(unsigned)nblk, UNC_THREADS, smem, st>>>(P, J);
   g_launches++;
   CK(cudaGetLastError());
   return UNC_OK;
+}
+
+int launch_grid(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
+  // two z per lane (64 z per CTA) halves the per-(a,p) work per point; keep one z per lane
+  // for short columns and when the larger totlap tile would not fit twice per SM
+  if (J.nz > 32 && P.np <= 53) return launch_grid_zl<2>(dev, P, J, st);
+  return launch_grid_zl<1>(dev, P, J, st);
 }
 
 // kernel selection: lanes<->z (grid kernel) once a column has enough z to fill most of a

@@ -16,7 +16,7 @@
 // collapse to 3-5 complex exponentials per (a,p) plus ONE per (a,p,z).  The algebra is
 // exact; only rounding differs, and the product forms avoid the cancellation the
 // reference's own expressions suffer (DESIGN.md "parity" discusses the noise floor).
-// Valid while Re(eta) <= UNC_FAST_ETA_MAX, where neither formulation can overflow;
+// Valid while Re(eta)*m <= UNC_FAST_EXP_MAX (fast_eta_max), where neither formulation can overflow;
 // beyond that the caller uses the literal path, which overflows exactly where the
 // reference does.
 #pragma once
@@ -26,7 +26,20 @@
 
 namespace unc {
 
-#define UNC_FAST_ETA_MAX 345.0  /* every intermediate of both formulations <= e^(2*345) < DBL_MAX */
+// Largest Re(eta)*m for which neither formulation overflows: the caller passes
+// eta_max = UNC_FAST_EXP_MAX / m, m = the largest exponent multiplier the REFERENCE's
+// literal formulas form for the z-values served (fast_eta_max() below).
+#define UNC_FAST_EXP_MAX 700.0
+
+// m: sinh(eta) -> 1; udp(zD=1) of models 3/5 and the layer-3 branch form
+// sinh(eta dD)*cosh(eta z) -> up to 1+dD (laplace_hankel_solutions.f90:179,81); layer-2
+// products stay below 1; |z| itself for callers outside 0<=zD<=1.
+__host__ __device__ __forceinline__ double fast_eta_max(const DevParams &P, int lay_mask, double zabs_max) {
+  double m = 1.0;
+  if (P.model == 3 || P.model == 5 || (lay_mask & 4)) m = 1.0 + P.dD;
+  if (zabs_max > m) m = zabs_max;
+  return UNC_FAST_EXP_MAX / m;
+}
 
 // Polynomial coefficients live in __constant__ memory so that DFMA takes them as
 // c[bank][offset] operands (ncu showed 35% of all issued instructions were UMOV/IMAD
@@ -213,8 +226,8 @@ struct Coef {  // f(z) = k0 + cp*exp(eta z) + cm*exp(-eta z)
 //   aux  : model 3: sum_m 1/(1+p/gamma_m);  model 2: A0(p) = 2/(p CDw K0 + xi K1)
 //   aux2 : model 2: p*tDb + 1
 __host__ __device__ __forceinline__ bool ap_terms_fast(const DevParams &P, cplx p, cplx aux, cplx aux2,
-                                              double a2, double w, int lay_mask, cplx *eta_out,
-                                              Coef *co /* [3], indexed by layer-1 */) {
+                                              double a2, double w, int lay_mask, double eta_max,
+                                              cplx *eta_out, Coef *co /* [3], indexed by layer-1 */) {
   const int model = P.model;
   const cplx pa = mk(p.re + a2, p.im);
   const cplx zero = mk(0.0, 0.0);
@@ -227,7 +240,7 @@ __host__ __device__ __forceinline__ bool ap_terms_fast(const DevParams &P, cplx 
   }
   const cplx eta = csqrt_pos(cscalef(pa, 1.0 / P.kappa));
   *eta_out = eta;
-  if (!(eta.re <= UNC_FAST_ETA_MAX && eta.im <= 2.0e5)) return false;  // sincos_q range
+  if (!(eta.re <= eta_max && eta.im <= 2.0e5)) return false;  // overflow bound; sincos_q range
   const cbundle E1 = cexp_bundle(eta.re, eta.im);
   cplx K0;  // common prefactor of the layer functions, weight folded in
   if (model == 2) K0 = cscalef(cdivf(aux, cmulf(pa, aux2)), w / P.bD);            // uDf/bD :265-266,299
@@ -238,7 +251,8 @@ __host__ __device__ __forceinline__ bool ap_terms_fast(const DevParams &P, cplx 
     for (int L = 0; L < 3; ++L) { co[L].k0 = K0; co[L].cp = zero; co[L].cm = zero; }
     top = K0;
   } else {
-    const cplx ish = crecipf(E1.sh);  // 1/sinh(eta)
+    // 1/sinh(eta); for Re(eta) > 20, sinh = e^eta (1 - e^-2eta)/2 with e^-2eta < 2^-57
+    const cplx ish = (eta.re > 20.0) ? cscalef(E1.em, 2.0) : crecipf(E1.sh);
     const double h = 0.5 * P.bD, m = 0.5 * (P.dD1 + P.lD1);
     const bool need13 = (lay_mask & 5) || model == 3 || model == 5;
     if (need13) {

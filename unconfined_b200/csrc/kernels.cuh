@@ -338,9 +338,16 @@ __device__ __noinline__ cplx wynn_dev(const cplx *series, int nacc) {
     cplx *cur = (j & 1) ? X : Y;   // column j
     cplx *oth = (j & 1) ? Y : X;   // column j-1 -> becomes j+1
     for (int m = 1; m <= ns - (j + 1); ++m) {
-      cplx denom = cur[m + 1] - cur[m];
-      if (cabs_d(denom) > eps) oth[m] = oth[m + 1] + 1.0 / denom;
-      else return cur[m + 1];
+      const cplx a = cur[m + 1], b = cur[m];
+      const double dr = a.re - b.re, di = a.im - b.im;
+      // abs(denom) > epsilon  <=>  |denom|^2 > eps^2 (no under/overflow in this range);
+      // 1/denom = conj(denom)/|denom|^2 (one division; rounding differs by ~1 ulp from Smith)
+      const double n2 = fma(dr, dr, di * di);
+      if (n2 > eps * eps) {
+        const double inv = 1.0 / n2;
+        const cplx o = oth[m + 1];
+        oth[m] = mk(fma(dr, inv, o.re), fma(-di, inv, o.im));
+      } else return a;
     }
   }
   return Y[2];
@@ -543,8 +550,10 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
   for (int i = 0; i < ZT; ++i) { zt[i] = s_z[i]; lt_[i] = s_lay[i]; }
 
   int lay_mask = 0;
+  double zabs = 0.0;
 #pragma unroll
-  for (int i = 0; i < ZT; ++i) if (i < nzt) lay_mask |= 1 << (lt_[i] - 1);
+  for (int i = 0; i < ZT; ++i) if (i < nzt) { lay_mask |= 1 << (lt_[i] - 1); zabs = fmax(zabs, fabs(zt[i])); }
+  const double eta_max = fast_eta_max(P, lay_mask, zabs);
 
   for (int pi = warp; pi < np; pi += UNC_WARPS) {
     cplx accT[ZT], accA[ZT], accB[ZT];
@@ -562,7 +571,7 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
         cplx f[ZT];
         cplx eta;
         Coef co[3];
-        if (ap_terms_fast(P, pp, aux, aux2, a2v, w, lay_mask, &eta, co)) {
+        if (ap_terms_fast(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, &eta, co)) {
 #pragma unroll
           for (int k = 0; k < ZT; ++k)
             if (k < nzt) {
@@ -672,11 +681,11 @@ struct StageEnt {
   Coef co[3];
 };
 
-__host__ __device__ inline size_t grid_smem_bytes(int np, int na_seq) {
+__host__ __device__ inline size_t grid_smem_bytes(int np, int na_seq, int ZL) {
   size_t b = 0;
   b += (size_t)4 * np * sizeof(cplx);                       // p, lt, aux, aux2
   b += (size_t)2 * na_seq * sizeof(double);                 // a2, wj
-  b += (size_t)np * 32 * sizeof(cplx);                      // totlap[p][lane]
+  b += (size_t)np * 32 * ZL * sizeof(cplx);                 // totlap[p][z]
   size_t stage = (size_t)UNC_WARPS * 32 * sizeof(StageEnt) + (size_t)UNC_WARPS * 32 * sizeof(int);
   size_t scratch = (size_t)UNC_WARPS * 3 * np * sizeof(cplx);  // de Hoog scratch aliases the stage
   b += stage > scratch ? stage : scratch;
@@ -684,17 +693,19 @@ __host__ __device__ inline size_t grid_smem_bytes(int np, int na_seq) {
   return (b + 15) & ~(size_t)15;
 }
 
+template <int ZL>
 __global__ void __launch_bounds__(UNC_THREADS, 2)
 lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job J) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int ZB = 32 * ZL;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int np = P.np, nacc = P.nacc, G = P.G, N = P.N;
   const int NA = N + nacc * G;
   const int na_seq = (NA + 31) & ~31;
-  const int nzb = (J.nz + 31) / 32;
+  const int nzb = (J.nz + ZB - 1) / ZB;
   const long long col = blockIdx.x / nzb;
-  const int z0 = (int)(blockIdx.x % nzb) * 32;
-  const int nzv = min(32, J.nz - z0);
+  const int z0 = (int)(blockIdx.x % nzb) * ZB;
+  const int nzv = min(ZB, J.nz - z0);
 
   unsigned char *sp = smem_raw;
   PTab T;
@@ -704,7 +715,7 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
   T.aux2 = (cplx *)sp; sp += np * sizeof(cplx);
   double *s_a2 = (double *)sp; sp += na_seq * sizeof(double);
   double *s_wj = (double *)sp; sp += na_seq * sizeof(double);
-  cplx *s_tot = (cplx *)sp; sp += (size_t)np * 32 * sizeof(cplx);
+  cplx *s_tot = (cplx *)sp; sp += (size_t)np * ZB * sizeof(cplx);
   StageEnt *s_stage = (StageEnt *)sp;
   int *s_ok = (int *)(sp + (size_t)UNC_WARPS * 32 * sizeof(StageEnt));
   cplx *s_scr = (cplx *)sp;
@@ -713,7 +724,7 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
     size_t scratch = (size_t)UNC_WARPS * 3 * np * sizeof(cplx);
     sp += stage > scratch ? stage : scratch;
   }
-  int *s_misc = (int *)sp;  // [0] layer mask, [1..] unused
+  int *s_misc = (int *)sp;  // [0] layer mask, [1] bits of max|z| (float)
 
   const double tD = J.tD[col / J.tdiv];
   const int sv = J.sv[col / J.tdiv];
@@ -722,12 +733,18 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
   const double arg = P.j0z[sv - 1] / rD;                      // driver.f90:120
   const double tscale = J.ts_scale ? J.ts_scale[col] : arg;  // driver.f90:121-126
   const long long zbase = (J.zstride ? col * (long long)J.nz : 0) + z0;
-  const bool zvalid = lane < nzv;
-  const double myz = zvalid ? J.zD[zbase + lane] : 0.5;
-  const int mylay = zvalid ? J.zLay[zbase + lane] : 2;
+  double myz[ZL];
+  int mylay[ZL];
+  bool zvalid[ZL];
+#pragma unroll
+  for (int k = 0; k < ZL; ++k) {
+    const int zi = lane + 32 * k;
+    zvalid[k] = zi < nzv;
+    myz[k] = zvalid[k] ? J.zD[zbase + zi] : 0.0;
+    mylay[k] = zvalid[k] ? J.zLay[zbase + zi] : 0;
+  }
 
   // ---- prologue ---------------------------------------------------------------
-  if (tid == 0) s_misc[0] = 0;
   for (int i = tid; i < np; i += UNC_THREADS) {
     const double PI = 3.141592653589793;
     double sigma = P.alpha - P.log_tol / (2.0 * tee);   // invlap.f90:166-170
@@ -764,24 +781,40 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
     s_a2[idx] = a * a;
     s_wj[idx] = (w != 0.0) ? w * (a * j0_dev(a * rD)) : 0.0;  // laplace_hankel_solutions.f90:118
   }
-  __syncthreads();
   if (warp == 0) {
-    int m = zvalid ? (1 << (mylay - 1)) : 0;
-    for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
-    if (lane == 0) s_misc[0] = m;
+    int m = 0;
+    float za = 0.f;
+#pragma unroll
+    for (int k = 0; k < ZL; ++k)
+      if (zvalid[k]) { m |= 1 << (mylay[k] - 1); za = fmaxf(za, (float)fabs(myz[k]) * 1.0000002f); }
+    for (int o = 16; o > 0; o >>= 1) {
+      m |= __shfl_xor_sync(0xffffffffu, m, o);
+      za = fmaxf(za, __shfl_xor_sync(0xffffffffu, za, o));
+    }
+    if (lane == 0) { s_misc[0] = m; s_misc[1] = __float_as_int(za); }
   }
   __syncthreads();
   const int lay_mask = s_misc[0];
-  const int myL = mylay - 1;
+  const double eta_max = fast_eta_max(P, lay_mask, (double)__int_as_float(s_misc[1]));
+  const bool uniform = (lay_mask & (lay_mask - 1)) == 0;   // one layer in the whole block
+  const int L0 = __ffs(lay_mask) - 1;
+  int myL[ZL];
+#pragma unroll
+  for (int k = 0; k < ZL; ++k) {
+    if (!zvalid[k]) { mylay[k] = L0 + 1; myz[k] = 0.5; }   // padding lanes mimic a present layer
+    myL[k] = mylay[k] - 1;
+  }
 
   // ---- phase A+B per p -----------------------------------------------------------
   StageEnt *stage = s_stage + warp * 32;
   int *okv = s_ok + warp * 32;
-  int stale = 0;
+  int stale = 0;  // bit k: z-slot k had an all-zero/NaN series for some p
   for (int pi = warp; pi < np; pi += UNC_WARPS) {
     const cplx pp = T.p[pi], aux = T.aux[pi], aux2 = T.aux2[pi];
-    cplx series[UNC_MAX_NACC];
-    cplx acc = mk(0.0, 0.0), fin = mk(0.0, 0.0);
+    cplx series[ZL][UNC_MAX_NACC];
+    cplx acc[ZL], fin[ZL];
+#pragma unroll
+    for (int k = 0; k < ZL; ++k) { acc[k] = mk(0.0, 0.0); fin[k] = mk(0.0, 0.0); }
     int seg = 0;        // 0: tanh-sinh, j>=1: Gauss-Lobatto interval j
     int next_b = N;     // first abscissa index of the next segment
     for (int base = 0; base < NA; base += 32) {
@@ -790,7 +823,7 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
         const int idx = base + lane;
         if (idx < NA) {
           StageEnt e;
-          ok = ap_terms_fast(P, pp, aux, aux2, s_a2[idx], s_wj[idx], lay_mask, &e.eta, e.co) ? 1 : 0;
+          ok = ap_terms_fast(P, pp, aux, aux2, s_a2[idx], s_wj[idx], lay_mask, eta_max, &e.eta, e.co) ? 1 : 0;
           stage[lane] = e;
         }
         okv[lane] = ok;
@@ -801,73 +834,96 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
       int j = 0;
       while (j < cnt) {
         const int jend = min(cnt, next_b - base);
-        if (all_ok) {
-          // hot loop: no branches, 4 broadcast LDS.128 + ~60 FP64 instructions per abscissa
-#pragma unroll 2
+        if (all_ok && uniform) {
+          // hot loop: 4 broadcast LDS.128 + ZL x ~59 FP64 instructions per abscissa, no branches
           for (; j < jend; ++j) {
             const cplx eta = stage[j].eta;
-            const Coef c = stage[j].co[myL];
-            acc = caddf(acc, eval_z_fast(eta, c, myz));
+            const Coef c = stage[j].co[L0];
+#pragma unroll
+            for (int k = 0; k < ZL; ++k) acc[k] = caddf(acc[k], eval_z_fast(eta, c, myz[k]));
+          }
+        } else if (all_ok) {
+          for (; j < jend; ++j) {
+            const cplx eta = stage[j].eta;
+#pragma unroll
+            for (int k = 0; k < ZL; ++k) acc[k] = caddf(acc[k], eval_z_fast(eta, stage[j].co[myL[k]], myz[k]));
           }
         } else {
           for (; j < jend; ++j) {
-            cplx f;
             if (okv[j]) {
-              f = eval_z_fast(stage[j].eta, stage[j].co[myL], myz);
+#pragma unroll
+              for (int k = 0; k < ZL; ++k)
+                acc[k] = caddf(acc[k], eval_z_fast(stage[j].eta, stage[j].co[myL[k]], myz[k]));
             } else {
               const int id = base + j;
-              cplx v = soln_literal_one(P, T, pi, s_a2[id], myz, mylay);
               const double w = s_wj[id];
-              f = mk(w * v.re, w * v.im);
+#pragma unroll
+              for (int k = 0; k < ZL; ++k) {
+                cplx v = soln_literal_one(P, T, pi, s_a2[id], myz[k], mylay[k]);
+                acc[k] = caddf(acc[k], mk(w * v.re, w * v.im));
+              }
             }
-            acc = caddf(acc, f);
           }
         }
         if (base + j == next_b && next_b < NA) {
-          if (seg == 0) fin = acc; else series[seg - 1] = acc;
-          acc = mk(0.0, 0.0);
+#pragma unroll
+          for (int k = 0; k < ZL; ++k) {
+            if (seg == 0) fin[k] = acc[k]; else series[k][seg - 1] = acc[k];
+            acc[k] = mk(0.0, 0.0);
+          }
           seg += 1;
           next_b += G;
         }
       }
       __syncwarp();
     }
-    if (seg == 0) fin = acc; else series[seg - 1] = acc;
+#pragma unroll
+    for (int k = 0; k < ZL; ++k) { if (seg == 0) fin[k] = acc[k]; else series[k][seg - 1] = acc[k]; }
     // phase B: Wynn-epsilon (integration.f90:125-189), totlap (driver.f90:216)
-    {
-      const double nan = __longlong_as_double(0x7ff8000000000000LL);
-      const cplx lt = T.lt[pi];
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const cplx lt = T.lt[pi];
+#pragma unroll
+    for (int k = 0; k < ZL; ++k) {
       bool any = false;
       for (int j = 0; j < nacc; ++j) {
-        cplx a = series[j];
+        cplx a = series[k][j];
         a = is_finite_c(a) ? a * lt : mk(nan, nan);
-        series[j] = a;
+        series[k][j] = a;
         if (cabs_d(a) > 0.0) any = true;  // driver.f90:209
       }
       cplx infint = mk(0.0, 0.0);
-      if (any) infint = wynn_dev(series, nacc);
-      else stale = 1;
-      fin = is_finite_c(fin) ? fin * lt : mk(nan, nan);
-      s_tot[pi * 32 + lane] = fin + infint;
+      if (any) infint = wynn_dev(series[k], nacc);
+      else stale |= 1 << k;
+      cplx f = fin[k];
+      f = is_finite_c(f) ? f * lt : mk(nan, nan);
+      s_tot[(size_t)pi * ZB + 32 * k + lane] = f + infint;
     }
   }
   // per-z stale flag: OR over the warps via shared memory
   __syncthreads();
   int *s_flag = (int *)s_scr;  // stage no longer needed
-  if (tid < 32) s_flag[tid] = 0;
+  if (tid < ZB) s_flag[tid] = 0;
   __syncthreads();
-  if (stale) atomicOr(&s_flag[lane], 1);
+#pragma unroll
+  for (int k = 0; k < ZL; ++k) if (stale & (1 << k)) atomicOr(&s_flag[32 * k + lane], 1);
   __syncthreads();
-  const int myflag = s_flag[lane];
+  int myflag[ZL];
+#pragma unroll
+  for (int k = 0; k < ZL; ++k) myflag[k] = s_flag[32 * k + lane];
   __syncthreads();
 
   // ---- phase C: de Hoog -------------------------------------------------------------
   cplx *scr = s_scr + (size_t)warp * 3 * np;
   for (int job = warp; job < 2 * nzv; job += UNC_WARPS) {
     const int zi = job >> 1, deriv = job & 1;
-    double v = dehoog_warp(P, s_tot + zi, 32, deriv ? T.p : nullptr, tD, tee, scr, scr + np,
+    double v = dehoog_warp(P, s_tot + zi, ZB, deriv ? T.p : nullptr, tD, tee, scr, scr + np,
                            scr + 2 * np, lane);
-    const int fl = __shfl_sync(0xffffffffu, myflag, zi);
+    int fl = 0;
+#pragma unroll
+    for (int k = 0; k < ZL; ++k) {
+      int f = __shfl_sync(0xffffffffu, myflag[k], zi & 31);
+      if ((zi >> 5) == k) fl = f;
+    }
     if (lane == 0) {
       const long long o = col * (long long)J.nz + z0 + zi;
       if (deriv) J.ds[o] = v * tD;  // driver.f90:228
