@@ -3,6 +3,7 @@
 // with the oracle at single (a,p,z) points.  Not linked into libunconfined_b200.so.
 #include <cstring>
 #include "../../unconfined_b200/csrc/fast.cuh"
+#include "../../unconfined_b200/csrc/wynn.cuh"
 
 extern "C" {
 
@@ -35,6 +36,14 @@ int hc_fast_soln(int model, double kappa, double alphaD, double beta, double lD,
 void hc_exp_pm(double x, double *out) {
   unc::rexp e = unc::exp_pm(x);
   out[0] = e.ep; out[1] = e.em; out[2] = e.ch; out[3] = e.sh;
+}
+
+// which: 0 = dispatcher used by the kernels, 1 = local-memory version, 2 = register version
+void hc_wynn(const double *series, int n, int which, double *out) {
+  unc::cplx s[UNC_MAX_NACC];
+  for (int i = 0; i < n; ++i) s[i] = unc::mk(series[2 * i], series[2 * i + 1]);
+  unc::cplx r = which == 1 ? unc::wynn_dev(s, n) : (which == 2 ? unc::wynn_reg<12>(s, n) : unc::wynn_any(s, n));
+  out[0] = r.re; out[1] = r.im;
 }
 
 void hc_sincos(double y, double *out) { unc::sincos_q(y, &out[0], &out[1]); }

@@ -158,3 +158,50 @@ def test_fast_path_is_closer_to_long_double_truth_than_the_double_literal(hc):
     e_lit = np.abs(ref_d[k] - truth) / np.abs(truth)
     assert e_fast.max() < 1e-12
     assert e_fast.max() <= e_lit.max() * 1.01 + 1e-15
+
+
+def _hc_wynn(hc, series, which):
+    s = np.ascontiguousarray(series, np.complex128)
+    out = (C.c_double * 2)()
+    hc.hc_wynn(s.view(np.float64).ctypes.data_as(C.POINTER(C.c_double)), len(s), which, out)
+    return complex(out[0], out[1])
+
+
+def test_device_wynn_matches_oracle_including_edge_semantics(hc):
+    """Both device implementations (local-memory column order, register 'moving lozenge')
+    against the oracle's restatement of integration.f90:125-189: full table, truncation,
+    sentinel, and the order-dependent |denom|<=epsilon early exit."""
+    rng = np.random.default_rng(5)
+    cases = []
+    for n in (2, 3, 4, 5, 7, 10, 11, 12):
+        for _ in range(6):
+            k = np.arange(n)
+            s = (-1.0) ** k / (k + 1 + rng.uniform(0, 2)) * (1 + 0.3j * rng.uniform(-1, 1, n))
+            cases.append(s)
+    # geometric (nearly exactly summable -> tiny denominators and 'epsilon cancel' exits)
+    for n in (6, 10, 12):
+        cases.append(np.array([0.5 ** i for i in range(n)], complex))
+        cases.append(np.array([(-0.25) ** i * (1 + 1j) for i in range(n)], complex))
+        cases.append(np.array([1.0, 0.5] + [1e-17 * 0.1 ** i for i in range(n - 2)], complex))
+        cases.append(np.array([1e-20 * (-0.5) ** i for i in range(n)], complex))   # everything below epsilon
+    # cancels placed at different (column,row) positions
+    base = np.array([(-1.0) ** i / (i + 1.0) for i in range(12)], complex)
+    for pos in range(2, 11):
+        s = base.copy(); s[pos] = 0.0
+        cases.append(s)
+        s = base.copy(); s[pos] = 1e-18; s[pos - 1] = 1e-18
+        cases.append(s)
+    # non-finite terms: truncation and sentinel
+    for pos in (0, 2, 3, 4, 5, 8, 11):
+        s = base.copy(); s[pos] = complex(np.inf, 0)
+        cases.append(s)
+        s = base.copy(); s[pos] = complex(0, np.nan)
+        cases.append(s)
+    n_cancel = 0
+    for s in cases:
+        want, info = oracle.wynn(s)
+        n_cancel += info == 3
+        for which in (0, 1, 2):
+            got = _hc_wynn(hc, s, which)
+            assert abs(got - want) <= 1e-12 * max(abs(want), 1e-300) + 1e-300, (which, info, s, got, want)
+    assert n_cancel >= 5        # the early-exit branch was really exercised

@@ -23,7 +23,7 @@ struct cplx {
 };
 
 __host__ __device__ __forceinline__ cplx mk(double r, double i) { cplx z; z.re = r; z.im = i; return z; }
-__device__ __forceinline__ cplx operator+(cplx a, cplx b) { return mk(a.re + b.re, a.im + b.im); }
+__host__ __device__ __forceinline__ cplx operator+(cplx a, cplx b) { return mk(a.re + b.re, a.im + b.im); }
 __device__ __forceinline__ cplx operator-(cplx a, cplx b) { return mk(a.re - b.re, a.im - b.im); }
 __device__ __forceinline__ cplx operator-(cplx a) { return mk(-a.re, -a.im); }
 __device__ __forceinline__ cplx operator*(cplx a, cplx b) {
@@ -61,9 +61,9 @@ __device__ __forceinline__ cplx fma_acc(double w, cplx f, cplx acc) {
   return mk(fma(w, f.re, acc.re), fma(w, f.im, acc.im));
 }
 
-__device__ __forceinline__ double cabs_d(cplx z) { return hypot(z.re, z.im); }
+__host__ __device__ __forceinline__ double cabs_d(cplx z) { return hypot(z.re, z.im); }
 // utility.f90:59-64
-__device__ __forceinline__ bool is_finite_c(cplx z) {
+__host__ __device__ __forceinline__ bool is_finite_c(cplx z) {
   double a = hypot(z.re, z.im);
   return !(isnan(a) || a > DBL_MAX);
 }

@@ -178,12 +178,28 @@ __host__ __device__ __forceinline__ void sincos_q(double y, double *sn, double *
   *cs = UNC_HILO2D(UNC_HIINT(b) ^ sb, UNC_LOINT(b));
 }
 
+// 1/x for x in the normal range: hardware approximation (MUFU.RCP64H, ~20 bits) + two
+// Newton steps (4 DFMA) instead of the ~25-instruction IEEE division sequence; <= 1 ulp.
+__host__ __device__ __forceinline__ double rcp_fast(double x) {
+#ifdef __CUDA_ARCH__
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+#else
+  return 1.0 / x;
+#endif
+}
+
 // plain complex helpers for finite operands (no real->complex promotion)
 __host__ __device__ __forceinline__ cplx cmulf(cplx a, cplx b) {
   return mk(fma(a.re, b.re, -(a.im * b.im)), fma(a.re, b.im, a.im * b.re));
 }
 __host__ __device__ __forceinline__ cplx crecipf(cplx b) {
-  const double d = 1.0 / fma(b.re, b.re, b.im * b.im);
+  const double d = rcp_fast(fma(b.re, b.re, b.im * b.im));
   return mk(b.re * d, -(b.im * d));
 }
 __host__ __device__ __forceinline__ cplx cdivf(cplx a, cplx b) { return cmulf(a, crecipf(b)); }
@@ -212,7 +228,7 @@ __host__ __device__ __forceinline__ cplx csqrt_pos(cplx z) {
   if (z.im == 0.0) return mk(sqrt(z.re), 0.0);
   const double d = sqrt(fma(z.re, z.re, z.im * z.im));
   const double r = sqrt(0.5 * (d + z.re));
-  return mk(r, 0.5 * (z.im / r));
+  return mk(r, 0.5 * (z.im * rcp_fast(r)));
 }
 
 struct Coef {  // f(z) = k0 + cp*exp(eta z) + cm*exp(-eta z)

@@ -18,6 +18,7 @@
 
 #include "params.cuh"
 #include "fast.cuh"
+#include "wynn.cuh"
 namespace unc {
 
 // ---------------------------------------------------------------------------
@@ -318,42 +319,6 @@ __device__ __noinline__ cplx soln_literal_one(const DevParams &P, const PTab &T,
 }
 
 // ---------------------------------------------------------------------------
-// integration.f90:125-189  wynn_epsilon on nacc terms (two live columns, in place)
-__device__ __noinline__ cplx wynn_dev(const cplx *series, int nacc) {
-  cplx X[UNC_MAX_NACC + 1], Y[UNC_MAX_NACC + 1];  // 1-based; X: odd columns (starts as col -1), Y: even
-  int ns = nacc;
-  cplx run = mk(0.0, 0.0);
-  for (int i = 1; i <= nacc; ++i) {
-    if (!is_finite_c(series[i - 1])) {
-      ns = i - 1;
-      break;
-    }
-    run = run + series[i - 1];
-    Y[i] = run;
-    X[i] = mk(0.0, 0.0);
-  }
-  if (ns < nacc && ns < 4) return mk(-999999.875, 0.0);  // real(4) literal -999999.9
-  const double eps = 2.220446049250313e-16;
-  for (int j = 0; j <= ns - 2; ++j) {
-    cplx *cur = (j & 1) ? X : Y;   // column j
-    cplx *oth = (j & 1) ? Y : X;   // column j-1 -> becomes j+1
-    for (int m = 1; m <= ns - (j + 1); ++m) {
-      const cplx a = cur[m + 1], b = cur[m];
-      const double dr = a.re - b.re, di = a.im - b.im;
-      // abs(denom) > epsilon  <=>  |denom|^2 > eps^2 (no under/overflow in this range);
-      // 1/denom = conj(denom)/|denom|^2 (one division; rounding differs by ~1 ulp from Smith)
-      const double n2 = fma(dr, dr, di * di);
-      if (n2 > eps * eps) {
-        const double inv = 1.0 / n2;
-        const cplx o = oth[m + 1];
-        oth[m] = mk(fma(dr, inv, o.re), fma(-di, inv, o.im));
-      } else return a;
-    }
-  }
-  return Y[2];
-}
-
-// ---------------------------------------------------------------------------
 // invlap.f90:46-141  de Hoog, Knight & Stokes for one time, executed by one warp.
 // f: np=2M+1 transform values (shared, stride fstride); if pmul != NULL each value is
 // multiplied by p first (driver.f90:228).  q,e,d: per-warp scratch of np complex each.
@@ -641,7 +606,7 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
         if (cabs_d(a) > 0.0) any = true;   // driver.f90:209
       }
       cplx infint = mk(0.0, 0.0);
-      if (any) infint = wynn_dev(series, nacc);
+      if (any) infint = wynn_any(series, nacc);
       else atomicOr(&s_flag[zi], 1);
       cplx fin = s_fin[k];
       fin = is_finite_c(fin) ? fin * lt : mk(nan, nan);
@@ -892,7 +857,7 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
         if (cabs_d(a) > 0.0) any = true;  // driver.f90:209
       }
       cplx infint = mk(0.0, 0.0);
-      if (any) infint = wynn_dev(series[k], nacc);
+      if (any) infint = wynn_any(series[k], nacc);
       else stale |= 1 << k;
       cplx f = fin[k];
       f = is_finite_c(f) ? f * lt : mk(nan, nan);

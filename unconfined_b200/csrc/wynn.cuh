@@ -1,0 +1,109 @@
+// Wynn-epsilon acceleration (integration.f90:125-189) for the kernels; host-compilable so
+// that tests/hostcheck can compare its edge semantics with the oracle on the CPU.
+#pragma once
+#include "params.cuh"
+#include "cmath.cuh"
+#include "fast.cuh"
+
+namespace unc {
+
+// ---------------------------------------------------------------------------
+// integration.f90:125-189  wynn_epsilon on nacc terms (two live columns, in place)
+__host__ __device__ __noinline__ cplx wynn_dev(const cplx *series, int nacc) {
+  cplx X[UNC_MAX_NACC + 1], Y[UNC_MAX_NACC + 1];  // 1-based; X: odd columns (starts as col -1), Y: even
+  int ns = nacc;
+  cplx run = mk(0.0, 0.0);
+  for (int i = 1; i <= nacc; ++i) {
+    if (!is_finite_c(series[i - 1])) {
+      ns = i - 1;
+      break;
+    }
+    run = run + series[i - 1];
+    Y[i] = run;
+    X[i] = mk(0.0, 0.0);
+  }
+  if (ns < nacc && ns < 4) return mk(-999999.875, 0.0);  // real(4) literal -999999.9
+  const double eps = 2.220446049250313e-16;
+  for (int j = 0; j <= ns - 2; ++j) {
+    cplx *cur = (j & 1) ? X : Y;   // column j
+    cplx *oth = (j & 1) ? Y : X;   // column j-1 -> becomes j+1
+    for (int m = 1; m <= ns - (j + 1); ++m) {
+      const cplx a = cur[m + 1], b = cur[m];
+      const double dr = a.re - b.re, di = a.im - b.im;
+      // abs(denom) > epsilon  <=>  |denom|^2 > eps^2 (no under/overflow in this range);
+      // 1/denom = conj(denom)/|denom|^2 (one division; rounding differs by ~1 ulp from Smith)
+      const double n2 = fma(dr, dr, di * di);
+      if (n2 > eps * eps) {
+        const double inv = rcp_fast(n2);
+        const cplx o = oth[m + 1];
+        oth[m] = mk(fma(dr, inv, o.re), fma(-di, inv, o.im));
+      } else return a;
+    }
+  }
+  return Y[2];
+}
+
+// The same algorithm with the epsilon table held in REGISTERS (north_star): anti-diagonal
+// ("moving lozenge") order needs only one entry per column, D[j] = eps(n-j, j) of the last
+// completed anti-diagonal n, instead of two full columns in local memory (which misses L1
+// here because shared memory takes most of it).  The reference fills the table column by
+// column and returns at the first |denom| <= epsilon in (column, row) order; in diagonal
+// order that is the cancel with the smallest column seen, earlier rows first, and once a
+// cancel is known only smaller columns still matter (jlim).  Fully unrolled for up to
+// NMAX terms with lane-private predicates.
+template <int NMAX>
+__host__ __device__ __forceinline__ cplx wynn_reg(const cplx *series, int nacc) {
+  int ns = nacc;
+  for (int i = 0; i < nacc; ++i)
+    if (!is_finite_c(series[i])) { ns = i; break; }
+  if (ns < nacc && ns < 4) return mk(-999999.875, 0.0);  // real(4) literal -999999.9
+  const double eps2 = 2.220446049250313e-16 * 2.220446049250313e-16;
+  cplx D[NMAX];
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) D[j] = mk(0.0, 0.0);
+  cplx run = mk(0.0, 0.0), best = mk(0.0, 0.0), keep_odd = mk(0.0, 0.0);
+  int jlim = NMAX;  // no cancel seen yet
+#pragma unroll
+  for (int n = 1; n <= NMAX; ++n) {
+    if (n <= ns) {
+      const cplx term = series[n - 1];
+      run = mk(run.re + term.re, run.im + term.im);  // eps(n,0) = sum(series(1:n))
+      cplx cur = run;
+      cplx pm1 = mk(0.0, 0.0);                        // eps(:,-1) = 0
+#pragma unroll
+      for (int j = 0; j <= n - 2; ++j) {
+        if (j < jlim) {
+          const cplx a = D[j];                        // eps(n-1-j, j)
+          if (n == ns && j == ns - 3) keep_odd = a;   // eps(2, ns-3)
+          D[j] = cur;                                 // eps(n-j, j)
+          const double dr = cur.re - a.re, di = cur.im - a.im;
+          const double n2 = fma(dr, dr, di * di);     // abs(denom) > epsilon(1.0)
+          if (n2 > eps2) {
+            const double inv = rcp_fast(n2);
+            cur = mk(fma(dr, inv, pm1.re), fma(-di, inv, pm1.im));  // eps(n-j-1, j+1)
+            pm1 = a;
+          } else {
+            best = cur;                               // reference returns eps(m+1, j)
+            jlim = j;
+          }
+        }
+      }
+      if (n - 1 < jlim) D[n - 1] = cur;
+    }
+  }
+  if (jlim < NMAX) return best;
+  if (ns & 1) return keep_odd;
+  cplx r = mk(0.0, 0.0);
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) if (j == ns - 2) r = D[j];
+  return r;
+}
+
+__host__ __device__ __forceinline__ cplx wynn_any(const cplx *series, int nacc) {
+#ifdef UNC_WYNN_REG
+  if (nacc <= 12) return wynn_reg<12>(series, nacc);
+#endif
+  return wynn_dev(series, nacc);
+}
+
+}  // namespace unc
