@@ -247,7 +247,8 @@ struct DevBuf {
 struct DevCtx {
   bool init = false;
   cudaStream_t stream = nullptr;
-  DevBuf tables, in, out;
+  DevBuf tables, in, out, scratch, counter;
+  int sm_count = 0;
   std::vector<double> blob_cached;
   bool smem_set[9] = {false};
 };
@@ -259,6 +260,7 @@ int ensure_ctx(int dev) {
   DevCtx &c = g_ctx[dev];
   if (!c.init) {
     CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CK(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev));
     c.init = true;
   }
   return UNC_OK;
@@ -326,7 +328,37 @@ int launch_grid_zl(int dev, const unc::DevParams &P, const unc::Job &J, cudaStre
   return UNC_OK;
 }
 
+// 128 z per work item, persistent CTAs drawing items from an atomic counter; totlap in a
+// per-CTA global scratch slot (kernels.cuh: lh_grid4_kernel)
+int launch_grid4(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
+  const int NA = P.N + P.nacc * P.G;
+  const size_t smem = unc::grid4_smem_bytes(P.np, (NA + 31) & ~31);
+  if (smem > 227 * 1024) return fail(UNC_ERR_UNSUPPORTED, "shared memory need %zu B exceeds 227 KB", smem);
+  DevCtx &c = g_ctx[dev];
+  if (!c.smem_set[5]) {
+    CK(cudaFuncSetAttribute(unc::lh_grid4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    c.smem_set[5] = true;
+  }
+  const long long nitems = J.ncol * ((J.nz + 127) / 128);
+  if (nitems <= 0) return UNC_OK;
+  if (nitems > 4000000000LL) return fail(UNC_ERR_UNSUPPORTED, "too many work items (%lld)", nitems);
+  const int grid = (int)std::min<long long>(nitems, (long long)c.sm_count * 2);
+  int rc = c.scratch.ensure((size_t)grid * P.np * 128 * sizeof(unc::cplx));
+  if (rc) return rc;
+  rc = c.counter.ensure(256);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(c.counter.ptr, 0, 4, st));
+  unc::lh_grid4_kernel<<<grid, UNC_THREADS, smem, st>>>(P, J, (unc::cplx *)c.scratch.ptr,
+                                                        (unsigned int *)c.counter.ptr);
+  g_launches++;
+  CK(cudaGetLastError());
+  return UNC_OK;
+}
+
 int launch_grid(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
+  const char *force = getenv("UNC_FORCE_KERNEL");
+  const bool no4 = force && !strcmp(force, "grid2");
+  if (J.nz >= 96 && !no4) return launch_grid4(dev, P, J, st);
   // two z per lane (64 z per CTA) halves the per-(a,p) work per point; keep one z per lane
   // for short columns and when the larger totlap tile would not fit twice per SM
   if (J.nz > 32 && P.np <= 53) return launch_grid_zl<2>(dev, P, J, st);
@@ -339,7 +371,7 @@ int launch(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st)
   const char *force = getenv("UNC_FORCE_KERNEL");
   bool grid = J.nz >= 12;
   if (force && !strcmp(force, "point")) grid = false;
-  if (force && !strcmp(force, "grid")) grid = true;
+  if (force && (!strcmp(force, "grid") || !strcmp(force, "grid2"))) grid = true;
   if (grid) return launch_grid(dev, P, J, st);
   if (J.nz >= 4) return launch_zt<4>(dev, P, J, st);
   if (J.nz >= 2) return launch_zt<2>(dev, P, J, st);
@@ -606,7 +638,7 @@ int unc_shutdown(void) {
     DevCtx &c = g_ctx[d];
     if (!c.init) continue;
     cudaSetDevice(d);
-    c.tables.release(); c.in.release(); c.out.release();
+    c.tables.release(); c.in.release(); c.out.release(); c.scratch.release(); c.counter.release();
     cudaStreamDestroy(c.stream);
     c = DevCtx();
   }

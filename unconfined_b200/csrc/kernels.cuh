@@ -901,6 +901,319 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
   }
 }
 
+// ---------------------------------------------------------------------------
+// Grid kernel, 128 z per work item, persistent CTAs.
+//
+// Same decomposition as lh_grid_kernel (lanes <-> z, one warp per p, per-(a,p) terms
+// staged 32 abscissae at a time) with three changes:
+//  * four z per lane (slots z0+lane+32k), so the per-(a,p) terms are shared by 128 z;
+//  * when the z of a lane's slots are equally spaced (contour grids: z = linspace), the
+//    exponentials of slots 1..3 follow from slot 0 by exp(eta(z+D)) = exp(eta z)*exp(eta D)
+//    with the per-(a,p) step exp(+-eta D) staged next to the coefficients: 18 instead of
+//    59 FP64 instructions per extra z.  Checked per CTA on the actual z (tolerance 4 ulp of
+//    max|z|: the induced error |eta|*4ulp is the size of the reference's own rounding of the
+//    product eta*zD); any other z-list takes the exact evaluation for every slot;
+//  * totlap (np x 128 complex = 108 KB for M=26) lives in a global scratch slot owned by the
+//    CTA (L2-resident) instead of shared memory, which keeps 2 CTAs (16 warps) per SM, and
+//    the CTAs are persistent: they draw (column, z-block) items from an atomic counter, so
+//    the few expensive columns (literal path at small rD) do not leave SMs idle.
+struct StageEnt4 {
+  cplx eta;
+  Coef co[3];
+  cplx sp, sm;  // exp(+eta*D), exp(-eta*D), D = z spacing between a lane's slots
+};
+
+__host__ __device__ inline size_t grid4_smem_bytes(int np, int na_seq) {
+  size_t b = 0;
+  b += (size_t)4 * np * sizeof(cplx);
+  b += (size_t)2 * na_seq * sizeof(double);
+  size_t stage = (size_t)UNC_WARPS * 32 * sizeof(StageEnt4) + (size_t)UNC_WARPS * 32 * sizeof(int);
+  size_t scratch = (size_t)UNC_WARPS * 3 * np * sizeof(cplx);
+  b += stage > scratch ? stage : scratch;
+  b += 128 * sizeof(int) + 64;
+  return (b + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ void eval4_recur(const StageEnt4 &e, const Coef &c0, const Coef &c1,
+                                            const Coef &c2, const Coef &c3, double z0, cplx *acc) {
+  double ep, em, cc, ss, s, cs;
+  int kk;
+  exp_pm_core(e.eta.re * z0, &ep, &em, &cc, &ss, &kk);
+  sincos_q(e.eta.im * z0, &s, &cs);
+  cplx Ep = mk(ep * cs, ep * s), Em = mk(em * cs, -(em * s));
+  const Coef *cf[4] = {&c0, &c1, &c2, &c3};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const Coef &c = *cf[k];
+    double fr = fma(c.cp.re, Ep.re, c.k0.re);
+    fr = fma(-c.cp.im, Ep.im, fr);
+    fr = fma(c.cm.re, Em.re, fr);
+    fr = fma(-c.cm.im, Em.im, fr);
+    double fi = fma(c.cp.re, Ep.im, c.k0.im);
+    fi = fma(c.cp.im, Ep.re, fi);
+    fi = fma(c.cm.re, Em.im, fi);
+    fi = fma(c.cm.im, Em.re, fi);
+    acc[k] = mk(acc[k].re + fr, acc[k].im + fi);
+    if (k < 3) { Ep = cmulf(Ep, e.sp); Em = cmulf(Em, e.sm); }
+  }
+}
+
+__global__ void __launch_bounds__(UNC_THREADS, 2)
+lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job J,
+                cplx *__restrict__ g_tot, unsigned int *__restrict__ g_counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int ZL = 4, ZB = 128;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int np = P.np, nacc = P.nacc, G = P.G, N = P.N;
+  const int NA = N + nacc * G;
+  const int na_seq = (NA + 31) & ~31;
+  const int nzb = (J.nz + ZB - 1) / ZB;
+  const long long nitems = J.ncol * (long long)nzb;
+
+  unsigned char *sp = smem_raw;
+  PTab T;
+  T.p = (cplx *)sp; sp += np * sizeof(cplx);
+  T.lt = (cplx *)sp; sp += np * sizeof(cplx);
+  T.aux = (cplx *)sp; sp += np * sizeof(cplx);
+  T.aux2 = (cplx *)sp; sp += np * sizeof(cplx);
+  double *s_a2 = (double *)sp; sp += na_seq * sizeof(double);
+  double *s_wj = (double *)sp; sp += na_seq * sizeof(double);
+  StageEnt4 *s_stage = (StageEnt4 *)sp;
+  int *s_ok = (int *)(sp + (size_t)UNC_WARPS * 32 * sizeof(StageEnt4));
+  cplx *s_scr = (cplx *)sp;
+  {
+    size_t stage = (size_t)UNC_WARPS * 32 * sizeof(StageEnt4) + (size_t)UNC_WARPS * 32 * sizeof(int);
+    size_t scratch = (size_t)UNC_WARPS * 3 * np * sizeof(cplx);
+    sp += stage > scratch ? stage : scratch;
+  }
+  int *s_flag = (int *)sp; sp += 128 * sizeof(int);
+  int *s_misc = (int *)sp;  // [0] layer mask, [1] max|z| bits, [2] uniform-z flag, [3..4] item, [5..6] D
+  cplx *tot = g_tot + (size_t)blockIdx.x * np * ZB;  // this CTA's totlap slot [p][z]
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int it = atomicAdd(g_counter, 1u);
+      s_misc[3] = (int)it;
+    }
+    __syncthreads();
+    const long long item = (unsigned int)s_misc[3];
+    if (item >= nitems) break;
+    const long long col = item / nzb;
+    const int z0 = (int)(item % nzb) * ZB;
+    const int nzv = min(ZB, J.nz - z0);
+
+    const double tD = J.tD[col / J.tdiv];
+    const int sv = J.sv[col / J.tdiv];
+    const double rD = J.rD[col % J.rmod];
+    const double tee = P.tee_mult * tD;
+    const double arg = P.j0z[sv - 1] / rD;                      // driver.f90:120
+    const double tscale = J.ts_scale ? J.ts_scale[col] : arg;  // driver.f90:121-126
+    const long long zbase = (J.zstride ? col * (long long)J.nz : 0) + z0;
+    double myz[ZL];
+    int mylay[ZL];
+    bool zvalid[ZL];
+#pragma unroll
+    for (int k = 0; k < ZL; ++k) {
+      const int zi = lane + 32 * k;
+      zvalid[k] = zi < nzv;
+      myz[k] = zvalid[k] ? J.zD[zbase + zi] : 0.0;
+      mylay[k] = zvalid[k] ? J.zLay[zbase + zi] : 0;
+    }
+
+    // ---- prologue -------------------------------------------------------------
+    if (tid < ZB) s_flag[tid] = 0;
+    for (int i = tid; i < np; i += UNC_THREADS) {
+      const double PI = 3.141592653589793;
+      double sigma = P.alpha - P.log_tol / (2.0 * tee);   // invlap.f90:166-170
+      cplx p = mk(sigma, PI * (double)i / tee);
+      T.p[i] = p;
+      T.lt[i] = laptime_dev(P, p);
+      cplx aux = mk(0.0, 0.0), aux2 = mk(0.0, 0.0);
+      if (P.model == 3) {
+        for (int m = 0; m < P.moench_M; ++m) aux = aux + 1.0 / (1.0 + p * (1.0 / P.moench_gamma[m]));
+      } else if (P.model == 2) {
+        cplx xi = P.rDw * csqrt_g(p);
+        cplx K[2];
+        cbesk01_dev(xi, K);
+        aux = 2.0 / (p * P.CDw * K[0] + xi * K[1]);
+        aux2 = p * P.tDb + 1.0;
+      }
+      T.aux[i] = aux;
+      T.aux2[i] = aux2;
+    }
+    for (int idx = tid; idx < na_seq; idx += UNC_THREADS) {
+      double a = 0.0, w = 0.0;
+      if (idx < N) {
+        a = (P.ts_T[idx] * tscale) / 2.0;  // integration.f90:62
+        w = P.ts_wc[idx] * (arg / 2.0);    // driver.f90:135,154 + Richardson (linear in tmp)
+      } else if (idx < NA) {
+        const int node = idx - N;
+        const int j = node / G, m = node - j * G;
+        const double lob = P.j0z[sv + j - 1] / rD;  // driver.f90:188-193
+        const double hib = P.j0z[sv + j] / rD;
+        const double width = hib - lob;
+        a = fma(width, P.gl_x[m], hib + lob) / 2.0;
+        w = P.gl_w[m] * (width / 2.0);
+      }
+      s_a2[idx] = a * a;
+      s_wj[idx] = (w != 0.0) ? w * (a * j0_dev(a * rD)) : 0.0;  // laplace_hankel_solutions.f90:118
+    }
+    if (warp == 0) {
+      int m = 0;
+      float za = 0.f;
+#pragma unroll
+      for (int k = 0; k < ZL; ++k)
+        if (zvalid[k]) { m |= 1 << (mylay[k] - 1); za = fmaxf(za, (float)fabs(myz[k]) * 1.0000002f); }
+      for (int o = 16; o > 0; o >>= 1) {
+        m |= __shfl_xor_sync(0xffffffffu, m, o);
+        za = fmaxf(za, __shfl_xor_sync(0xffffffffu, za, o));
+      }
+      // equally spaced slots?  D from lane 0 (slots 0,1 are always valid when nz >= 64)
+      const double D = __shfl_sync(0xffffffffu, myz[1] - myz[0], 0);
+      const double tol = 4.0 * 2.220446049250313e-16 * (double)za;
+      bool uni = __shfl_sync(0xffffffffu, (int)(zvalid[0] && zvalid[1]), 0) != 0;
+#pragma unroll
+      for (int k = 0; k + 1 < ZL; ++k)
+        if (zvalid[k] && zvalid[k + 1] && !(fabs((myz[k + 1] - myz[k]) - D) <= tol)) uni = false;
+      uni = __all_sync(0xffffffffu, uni);
+      if (lane == 0) {
+        s_misc[0] = m;
+        s_misc[1] = __float_as_int(za);
+        s_misc[2] = uni ? 1 : 0;
+        *(double *)(s_misc + 6) = D;
+      }
+    }
+    __syncthreads();
+    const int lay_mask = s_misc[0];
+    const double eta_max = fast_eta_max(P, lay_mask, (double)__int_as_float(s_misc[1]));
+    const bool zuni = s_misc[2] != 0;
+    const double Dz = *(double *)(s_misc + 6);
+    const int L0 = __ffs(lay_mask) - 1;
+    int myL[ZL];
+#pragma unroll
+    for (int k = 0; k < ZL; ++k) {
+      if (!zvalid[k]) {                 // padding slots mimic a present layer / the uniform grid
+        mylay[k] = L0 + 1;
+        myz[k] = zuni ? myz[0] + k * Dz : 0.5;
+        if (!zvalid[0]) myz[k] = 0.5;
+      }
+      myL[k] = mylay[k] - 1;
+    }
+
+    // ---- phase A+B per p ---------------------------------------------------------
+    StageEnt4 *stage = s_stage + warp * 32;
+    int *okv = s_ok + warp * 32;
+    int stale = 0;
+    for (int pi = warp; pi < np; pi += UNC_WARPS) {
+      const cplx pp = T.p[pi], aux = T.aux[pi], aux2 = T.aux2[pi];
+      cplx series[ZL][UNC_MAX_NACC];
+      cplx acc[ZL], fin[ZL];
+#pragma unroll
+      for (int k = 0; k < ZL; ++k) { acc[k] = mk(0.0, 0.0); fin[k] = mk(0.0, 0.0); }
+      int seg = 0;
+      int next_b = N;
+      for (int base = 0; base < NA; base += 32) {
+        int ok = 1;
+        {
+          const int idx = base + lane;
+          if (idx < NA) {
+            StageEnt4 e;
+            ok = ap_terms_fast(P, pp, aux, aux2, s_a2[idx], s_wj[idx], lay_mask, eta_max, &e.eta, e.co) ? 1 : 0;
+            if (zuni && ok) {
+              const cbundle S = cexp_bundle(e.eta.re * Dz, e.eta.im * Dz);
+              e.sp = S.ep;
+              e.sm = S.em;
+            } else { e.sp = mk(1.0, 0.0); e.sm = mk(1.0, 0.0); }
+            stage[lane] = e;
+          }
+          okv[lane] = ok;
+        }
+        const bool all_ok = __all_sync(0xffffffffu, ok);
+        __syncwarp();
+        const int cnt = min(32, NA - base);
+        int j = 0;
+        while (j < cnt) {
+          const int jend = min(cnt, next_b - base);
+          if (all_ok && zuni) {
+            // hot loop: one exp+sincos for slot 0, complex-multiply recurrence for slots 1..3
+            for (; j < jend; ++j) {
+              const StageEnt4 &e = stage[j];
+              eval4_recur(e, e.co[myL[0]], e.co[myL[1]], e.co[myL[2]], e.co[myL[3]], myz[0], acc);
+            }
+          } else {
+            for (; j < jend; ++j) {
+              if (okv[j]) {
+#pragma unroll
+                for (int k = 0; k < ZL; ++k)
+                  acc[k] = caddf(acc[k], eval_z_fast(stage[j].eta, stage[j].co[myL[k]], myz[k]));
+              } else {
+                const int id = base + j;
+                const double w = s_wj[id];
+#pragma unroll
+                for (int k = 0; k < ZL; ++k) {
+                  cplx v = soln_literal_one(P, T, pi, s_a2[id], myz[k], mylay[k]);
+                  acc[k] = caddf(acc[k], mk(w * v.re, w * v.im));
+                }
+              }
+            }
+          }
+          if (base + j == next_b && next_b < NA) {
+#pragma unroll
+            for (int k = 0; k < ZL; ++k) {
+              if (seg == 0) fin[k] = acc[k]; else series[k][seg - 1] = acc[k];
+              acc[k] = mk(0.0, 0.0);
+            }
+            seg += 1;
+            next_b += G;
+          }
+        }
+        __syncwarp();
+      }
+#pragma unroll
+      for (int k = 0; k < ZL; ++k) { if (seg == 0) fin[k] = acc[k]; else series[k][seg - 1] = acc[k]; }
+      const double nan = __longlong_as_double(0x7ff8000000000000LL);
+      const cplx lt = T.lt[pi];
+#pragma unroll
+      for (int k = 0; k < ZL; ++k) {
+        bool any = false;
+        for (int j = 0; j < nacc; ++j) {
+          cplx a = series[k][j];
+          a = is_finite_c(a) ? a * lt : mk(nan, nan);
+          series[k][j] = a;
+          if (cabs_d(a) > 0.0) any = true;  // driver.f90:209
+        }
+        cplx infint = mk(0.0, 0.0);
+        if (any) infint = wynn_any(series[k], nacc);
+        else stale |= 1 << k;
+        cplx f = fin[k];
+        f = is_finite_c(f) ? f * lt : mk(nan, nan);
+        tot[(size_t)pi * ZB + 32 * k + lane] = f + infint;   // totlap, driver.f90:216
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < ZL; ++k) if (stale & (1 << k)) atomicOr(&s_flag[32 * k + lane], 1);
+    __syncthreads();   // totlap (global, this CTA's slot) and flags complete
+
+    // ---- phase C: de Hoog ---------------------------------------------------------
+    cplx *scr = s_scr + (size_t)warp * 3 * np;
+    for (int job = warp; job < 2 * nzv; job += UNC_WARPS) {
+      const int zi = job >> 1, deriv = job & 1;
+      double v = dehoog_warp(P, tot + zi, ZB, deriv ? T.p : nullptr, tD, tee, scr, scr + np,
+                             scr + 2 * np, lane);
+      if (lane == 0) {
+        const long long o = col * (long long)J.nz + z0 + zi;
+        if (deriv) J.ds[o] = v * tD;  // driver.f90:228
+        else {
+          J.s[o] = v;
+          if (J.flags) J.flags[o] = s_flag[zi];
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // DFMA-chain microbenchmark: 8 independent chains per thread
 __global__ void fp64_peak_kernel(double *out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
