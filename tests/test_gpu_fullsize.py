@@ -86,3 +86,40 @@ def test_grid_kernel_equals_point_kernel_on_sample(c5a):
     # except where the result itself is rounding noise (tiny early-time drawdowns)
     assert np.median(rel) < 1e-12
     assert (rel < 1e-6).mean() > 0.98
+
+
+def test_small_radius_columns_overflow_flow_matches_oracle(c5a):
+    """The few smallest radii of the C5a grid are where the reference's cosh/sinh overflow:
+    Wynn truncation, sentinel and stale flags of the 128-z persistent kernel (which stops
+    evaluating a p once every z's series is settled) must match the oracle exactly, and the
+    finite results must agree."""
+    g = c5a
+    ir = np.arange(0, 12)
+    it = np.array([1, 6])
+    po = oracle.Params(g["p"])
+    so, do, fo = oracle.eval_grid(po, g["tD"][it], g["sv"][it], g["rD"][ir], g["zD"], g["lay"], carry=False)
+    sg, dg, fg = g["s"][it][:, ir], g["ds"][it][:, ir], g["fl"][it][:, ir]
+    assert np.array_equal(fo, fg)
+    assert np.array_equal(np.isnan(so), np.isnan(sg))
+    sent = np.abs(so) > 1e4          # sentinel-dominated: -999999.9 passed through de Hoog
+    assert sent.any()
+    ok = np.isfinite(so)
+    rel = np.abs(sg[ok] - so[ok]) / np.maximum(np.abs(so[ok]), 1e-300)
+    assert np.median(rel) < 1e-11
+    assert (rel < 1e-6).mean() > 0.97
+
+
+def test_grid4_equals_grid2_kernel_bitwise_semantics(c5a):
+    """The persistent 128-z kernel and the 64-z kernel implement the same arithmetic except
+    for the z-recurrence of the exponentials: results agree far below the parity bar."""
+    g = c5a
+    os.environ["UNC_FORCE_KERNEL"] = "grid2"
+    try:
+        s2, d2, f2 = ub.eval_grid(g["prm"], g["tD"][2:4], g["sv"][2:4], g["rD"][::16], g["zD"], g["lay"], want_flags=True)
+    finally:
+        os.environ.pop("UNC_FORCE_KERNEL", None)
+    s4, f4 = g["s"][2:4][:, ::16], g["fl"][2:4][:, ::16]
+    assert np.array_equal(f2, f4)
+    ok = np.isfinite(s2) & np.isfinite(s4)
+    rel = np.abs(s4[ok] - s2[ok]) / np.maximum(np.abs(s2[ok]), 1e-300)
+    assert np.median(rel) < 1e-12 and (rel < 1e-7).mean() > 0.98

@@ -250,7 +250,7 @@ struct DevCtx {
   DevBuf tables, in, out, scratch, counter;
   int sm_count = 0;
   std::vector<double> blob_cached;
-  bool smem_set[9] = {false};
+  bool smem_set[16] = {false};
 };
 DevCtx g_ctx[16];
 
@@ -315,9 +315,9 @@ int launch_grid_zl(int dev, const unc::DevParams &P, const unc::Job &J, cudaStre
   const size_t smem = unc::grid_smem_bytes(P.np, (NA + 31) & ~31, ZL);
   if (smem > 227 * 1024) return fail(UNC_ERR_UNSUPPORTED, "shared memory need %zu B exceeds 227 KB", smem);
   DevCtx &c = g_ctx[dev];
-  if (!c.smem_set[6 + ZL]) {
+  if (!c.smem_set[10 + ZL]) {
     CK(cudaFuncSetAttribute(unc::lh_grid_kernel<ZL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    c.smem_set[6 + ZL] = true;
+    c.smem_set[10 + ZL] = true;
   }
   const long long nblk = J.ncol * ((J.nz + 32 * ZL - 1) / (32 * ZL));
   if (nblk <= 0) return UNC_OK;
@@ -330,29 +330,39 @@ int launch_grid_zl(int dev, const unc::DevParams &P, const unc::Job &J, cudaStre
 
 // 128 z per work item, persistent CTAs drawing items from an atomic counter; totlap in a
 // per-CTA global scratch slot (kernels.cuh: lh_grid4_kernel)
-int launch_grid4(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
+template <int NW>
+int launch_grid4_nw(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
   const int NA = P.N + P.nacc * P.G;
-  const size_t smem = unc::grid4_smem_bytes(P.np, (NA + 31) & ~31);
+  const size_t smem = unc::grid4_smem_bytes(P.np, (NA + 31) & ~31, NW);
   if (smem > 227 * 1024) return fail(UNC_ERR_UNSUPPORTED, "shared memory need %zu B exceeds 227 KB", smem);
   DevCtx &c = g_ctx[dev];
-  if (!c.smem_set[5]) {
-    CK(cudaFuncSetAttribute(unc::lh_grid4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    c.smem_set[5] = true;
+  if (!c.smem_set[NW % 9]) {
+    CK(cudaFuncSetAttribute(unc::lh_grid4_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    c.smem_set[NW % 9] = true;
   }
   const long long nitems = J.ncol * ((J.nz + 127) / 128);
   if (nitems <= 0) return UNC_OK;
   if (nitems > 4000000000LL) return fail(UNC_ERR_UNSUPPORTED, "too many work items (%lld)", nitems);
-  const int grid = (int)std::min<long long>(nitems, (long long)c.sm_count * 2);
+  int occ = 2;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, unc::lh_grid4_kernel<NW>, NW * 32, smem));
+  if (occ < 1) occ = 1;
+  const int grid = (int)std::min<long long>(nitems, (long long)c.sm_count * occ);
   int rc = c.scratch.ensure((size_t)grid * P.np * 128 * sizeof(unc::cplx));
   if (rc) return rc;
   rc = c.counter.ensure(256);
   if (rc) return rc;
   CK(cudaMemsetAsync(c.counter.ptr, 0, 4, st));
-  unc::lh_grid4_kernel<<<grid, UNC_THREADS, smem, st>>>(P, J, (unc::cplx *)c.scratch.ptr,
-                                                        (unsigned int *)c.counter.ptr);
+  unc::lh_grid4_kernel<NW><<<grid, NW * 32, smem, st>>>(P, J, (unc::cplx *)c.scratch.ptr,
+                                                         (unsigned int *)c.counter.ptr);
   g_launches++;
   CK(cudaGetLastError());
   return UNC_OK;
+}
+
+int launch_grid4(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
+  const char *nw = getenv("UNC_GRID4_WARPS");
+  if (nw && atoi(nw) == 7) return launch_grid4_nw<7>(dev, P, J, st);
+  return launch_grid4_nw<8>(dev, P, J, st);
 }
 
 int launch_grid(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
@@ -558,6 +568,15 @@ int run_host(const unc_params *prm, const HostJob &hj, int ngpu) {
 }  // namespace
 
 extern "C" {
+
+#ifdef UNC_PROFILE
+int unc_debug_profile(unsigned long long *out, int reset) {
+  unsigned long long z[16] = {0};
+  if (out) cudaMemcpyFromSymbol(out, unc::g_prof, sizeof z);
+  if (reset) cudaMemcpyToSymbol(unc::g_prof, z, sizeof z);
+  return 0;
+}
+#endif
 
 const char *unc_version(void) { return "unconfined_b200 0.1 (sm_100a)"; }
 const char *unc_last_error(void) { return g_err.c_str(); }

@@ -68,6 +68,12 @@ __host__ __device__ __forceinline__ bool is_finite_c(cplx z) {
   return !(isnan(a) || a > DBL_MAX);
 }
 
+// same predicate without the hypot call when both components are far from overflow
+__host__ __device__ __forceinline__ bool is_finite_fastc(cplx z) {
+  if (fabs(z.re) < 1e150 && fabs(z.im) < 1e150) return true;   // false for NaN
+  return is_finite_c(z);
+}
+
 // ---- glibc-shaped complex elementary functions (finite arguments) ----------
 #define UNC_EXP_T 709  /* (int)((DBL_MAX_EXP-1)*M_LN2) */
 

@@ -391,6 +391,93 @@ __device__ __noinline__ double dehoog_warp(const DevParams &P, const cplx *f, in
   return exp(gamma * t) / tee * (A2M / B2M).re;
 }
 
+// The same inversion done by ONE thread (lane-parallel over inversions): the warp version
+// above keeps 32 lanes on a <=53-entry row and pays ~7000 warp instructions per inversion;
+// with one inversion per lane the q-d table is two thread-local columns updated in place
+// (e(i,r) and q(i,r+1) only read entries at i and i+1 of the previous column).
+__device__ __noinline__ double dehoog_lane(const DevParams &P, const cplx *f, int fstride,
+                                           const cplx *pmul, double t, double tee) {
+  const int M = P.M, n2 = 2 * M;
+  cplx q[2 * 31 + 2], e[2 * 31 + 2], d[2 * 31 + 2];
+  double mx = -1.0;
+  bool anynum = false;
+  for (int i = 0; i <= n2; ++i) {
+    cplx v = f[(size_t)i * fstride];
+    if (pmul) v = v * pmul[i];
+    double a = hypot(v.re, v.im);
+    if (!isnan(a)) { anynum = true; mx = fmax(mx, a); }
+    if (isnan(v.re) || isnan(v.im)) v = mk(0.0, 0.0);
+    d[i] = v;
+    e[i] = mk(0.0, 0.0);
+  }
+  if (!anynum || !(mx > DBL_MIN)) return 0.0;
+  q[0] = d[1] / (d[0] / 2.0);
+  for (int i = 1; i <= n2 - 1; ++i) q[i] = d[i + 1] / d[i];
+  d[0] = d[0] / 2.0;
+  // rows are processed in register blocks of UB entries so that the thread-local loads of a
+  // block are all in flight together (the table lives in L2-backed local memory)
+  constexpr int UB = 6;
+  for (int r = 1; r <= M; ++r) {
+    int mxi = 2 * (M - r);
+    cplx qi = q[0];
+    d[2 * r - 1] = -qi;
+    for (int i0 = 0; i0 <= mxi; i0 += UB) {
+      cplx qn[UB], en[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int i = min(i0 + u, mxi);          // clamped loads stay inside the row
+        qn[u] = q[i + 1];
+        en[u] = e[i + 1];
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        if (i0 + u <= mxi) {
+          e[i0 + u] = qn[u] - qi + en[u];
+          qi = qn[u];
+        }
+      }
+    }
+    d[2 * r] = -e[0];
+    if (r != M) {
+      mxi = 2 * (M - (r + 1)) + 1;
+      cplx ei = e[0];
+      for (int i0 = 0; i0 <= mxi; i0 += UB) {
+        cplx qn[UB], en[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int i = min(i0 + u, mxi);
+          qn[u] = q[i + 1];
+          en[u] = e[i + 1];
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          if (i0 + u <= mxi) {
+            q[i0 + u] = qn[u] * en[u] / ei;
+            ei = en[u];
+          }
+        }
+      }
+    }
+  }
+  const double PI = 3.141592653589793;
+  double sn, cs;
+  sincos_g((PI * t) / tee, &sn, &cs);
+  const cplx zz = mk(cs, sn);
+  cplx Am2 = mk(0.0, 0.0), Am1 = d[0], Bm2 = mk(1.0, 0.0), Bm1 = mk(1.0, 0.0);
+  for (int n = 1; n <= n2 - 1; ++n) {
+    const cplx dn = d[n];
+    cplx An = Am1 + dn * Am2 * zz;
+    cplx Bn = Bm1 + dn * Bm2 * zz;
+    Am2 = Am1; Am1 = An; Bm2 = Bm1; Bm1 = Bn;
+  }
+  cplx brem = (1.0 + (d[n2 - 1] - d[n2]) * zz) / 2.0;
+  cplx rem = (-brem) * (1.0 - csqrt_g(1.0 + d[n2] * zz / (brem * brem)));
+  cplx A2M = Am1 + rem * Am2;
+  cplx B2M = Bm1 + rem * Bm2;
+  const double gamma = P.alpha - P.log_tol / (2.0 * tee);
+  return exp(gamma * t) / tee * (A2M / B2M).re;
+}
+
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double shfl_down_d(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ double shfl_xor_d(double v, int d) { return __shfl_xor_sync(0xffffffffu, v, d); }
@@ -917,18 +1004,27 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
 //    CTA (L2-resident) instead of shared memory, which keeps 2 CTAs (16 warps) per SM, and
 //    the CTAs are persistent: they draw (column, z-block) items from an atomic counter, so
 //    the few expensive columns (literal path at small rD) do not leave SMs idle.
+#ifdef UNC_PROFILE
+__device__ unsigned long long g_prof[16];
+#define PROF_T0() long long _t0 = clock64()
+#define PROF_ADD(i) do { long long _t1 = clock64(); if (lane == 0) atomicAdd(&g_prof[i], (unsigned long long)(_t1 - _t0)); _t0 = _t1; } while (0)
+#else
+#define PROF_T0()
+#define PROF_ADD(i)
+#endif
+
 struct StageEnt4 {
   cplx eta;
   Coef co[3];
   cplx sp, sm;  // exp(+eta*D), exp(-eta*D), D = z spacing between a lane's slots
 };
 
-__host__ __device__ inline size_t grid4_smem_bytes(int np, int na_seq) {
+__host__ __device__ inline size_t grid4_smem_bytes(int np, int na_seq, int NW) {
   size_t b = 0;
   b += (size_t)4 * np * sizeof(cplx);
   b += (size_t)2 * na_seq * sizeof(double);
-  size_t stage = (size_t)UNC_WARPS * 32 * sizeof(StageEnt4) + (size_t)UNC_WARPS * 32 * sizeof(int);
-  size_t scratch = (size_t)UNC_WARPS * 3 * np * sizeof(cplx);
+  size_t stage = (size_t)NW * 32 * sizeof(StageEnt4) + (size_t)NW * 32 * sizeof(int);
+  size_t scratch = (size_t)NW * 3 * np * sizeof(cplx);
   b += stage > scratch ? stage : scratch;
   b += 128 * sizeof(int) + 64;
   return (b + 15) & ~(size_t)15;
@@ -958,7 +1054,65 @@ __device__ __forceinline__ void eval4_recur(const StageEnt4 &e, const Coef &c0, 
   }
 }
 
-__global__ void __launch_bounds__(UNC_THREADS, 2)
+// The hot loop as separate functions: the persistent kernel around it keeps ~100 registers
+// of long-lived state, and inlined there the loop was compiled with address
+// rematerialisation (S2R/R2UR) and extra loads; as a call it gets its own register
+// allocation (the isolated loop runs at 98% of the FP64 pipe, tools/micro/hotloop_bench.cu).
+// acc lives in the caller's local memory only across the call.
+__device__ __noinline__ void hot_run_same(const StageEnt4 *stage, int j, int jend, double z0, int L,
+                                          cplx *acc_io) {
+  cplx acc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc[k] = acc_io[k];
+  for (; j < jend; ++j) {
+    const StageEnt4 &e = stage[j];
+    const Coef c = e.co[L];
+    eval4_recur(e, c, c, c, c, z0, acc);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc_io[k] = acc[k];
+}
+
+__device__ __noinline__ void hot_run_mixed(const StageEnt4 *stage, int j, int jend, double z0,
+                                           int Lpack, cplx *acc_io) {
+  cplx acc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc[k] = acc_io[k];
+  const int l0 = Lpack & 3, l1 = (Lpack >> 2) & 3, l2 = (Lpack >> 4) & 3, l3 = (Lpack >> 6) & 3;
+  for (; j < jend; ++j) {
+    const StageEnt4 &e = stage[j];
+    eval4_recur(e, e.co[l0], e.co[l1], e.co[l2], e.co[l3], z0, acc);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc_io[k] = acc[k];
+}
+
+// Per-(a,p) terms written straight into the shared-memory stage entry.  A separate function
+// on purpose: inlined into the persistent kernel it was compiled under that kernel's
+// register pressure, spilled ~1 KB per call to L2-backed local memory and cost 2/3 of the
+// step (phase ablation, tools/micro/run_variants.sh); as a call it has its own allocation.
+__device__ __noinline__ int ap_terms_stage(const DevParams &P, cplx p, cplx aux, cplx aux2, double a2,
+                                           double w, int lay_mask, double eta_max, bool zuni,
+                                           double Dz, StageEnt4 *out) {
+  StageEnt4 e;
+  const bool ok = ap_terms_fast(P, p, aux, aux2, a2, w, lay_mask, eta_max, &e.eta, e.co);
+  if (zuni && ok) {
+    const cbundle S = cexp_bundle(e.eta.re * Dz, e.eta.im * Dz);
+    e.sp = S.ep;
+    e.sm = S.em;
+  } else {
+    e.sp = mk(1.0, 0.0);
+    e.sm = mk(1.0, 0.0);
+  }
+  *out = e;
+  return ok ? 1 : 0;
+}
+
+#ifndef UNC_GRID4_MINB
+#define UNC_GRID4_MINB 2
+#endif
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, UNC_GRID4_MINB)
 lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job J,
                 cplx *__restrict__ g_tot, unsigned int *__restrict__ g_counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -979,19 +1133,21 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
   double *s_a2 = (double *)sp; sp += na_seq * sizeof(double);
   double *s_wj = (double *)sp; sp += na_seq * sizeof(double);
   StageEnt4 *s_stage = (StageEnt4 *)sp;
-  int *s_ok = (int *)(sp + (size_t)UNC_WARPS * 32 * sizeof(StageEnt4));
+  int *s_ok = (int *)(sp + (size_t)NW * 32 * sizeof(StageEnt4));
   cplx *s_scr = (cplx *)sp;
   {
-    size_t stage = (size_t)UNC_WARPS * 32 * sizeof(StageEnt4) + (size_t)UNC_WARPS * 32 * sizeof(int);
-    size_t scratch = (size_t)UNC_WARPS * 3 * np * sizeof(cplx);
+    size_t stage = (size_t)NW * 32 * sizeof(StageEnt4) + (size_t)NW * 32 * sizeof(int);
+    size_t scratch = (size_t)NW * 3 * np * sizeof(cplx);
     sp += stage > scratch ? stage : scratch;
   }
   int *s_flag = (int *)sp; sp += 128 * sizeof(int);
   int *s_misc = (int *)sp;  // [0] layer mask, [1] max|z| bits, [2] uniform-z flag, [3..4] item, [5..6] D
   cplx *tot = g_tot + (size_t)blockIdx.x * np * ZB;  // this CTA's totlap slot [p][z]
 
+  PROF_T0();
   for (;;) {
     __syncthreads();
+    PROF_ADD(0);
     if (tid == 0) {
       unsigned int it = atomicAdd(g_counter, 1u);
       s_misc[3] = (int)it;
@@ -1023,7 +1179,7 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
 
     // ---- prologue -------------------------------------------------------------
     if (tid < ZB) s_flag[tid] = 0;
-    for (int i = tid; i < np; i += UNC_THREADS) {
+    for (int i = tid; i < np; i += NW * 32) {
       const double PI = 3.141592653589793;
       double sigma = P.alpha - P.log_tol / (2.0 * tee);   // invlap.f90:166-170
       cplx p = mk(sigma, PI * (double)i / tee);
@@ -1042,7 +1198,7 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       T.aux[i] = aux;
       T.aux2[i] = aux2;
     }
-    for (int idx = tid; idx < na_seq; idx += UNC_THREADS) {
+    for (int idx = tid; idx < na_seq; idx += NW * 32) {
       double a = 0.0, w = 0.0;
       if (idx < N) {
         a = (P.ts_T[idx] * tscale) / 2.0;  // integration.f90:62
@@ -1085,6 +1241,7 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       }
     }
     __syncthreads();
+    PROF_ADD(1);
     const int lay_mask = s_misc[0];
     const double eta_max = fast_eta_max(P, lay_mask, (double)__int_as_float(s_misc[1]));
     const bool zuni = s_misc[2] != 0;
@@ -1101,11 +1258,14 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       myL[k] = mylay[k] - 1;
     }
 
+    const int Lpack = myL[0] | (myL[1] << 2) | (myL[2] << 4) | (myL[3] << 6);
+    const bool same_layer = (lay_mask & (lay_mask - 1)) == 0;   // one layer in the whole block
+
     // ---- phase A+B per p ---------------------------------------------------------
     StageEnt4 *stage = s_stage + warp * 32;
     int *okv = s_ok + warp * 32;
     int stale = 0;
-    for (int pi = warp; pi < np; pi += UNC_WARPS) {
+    for (int pi = warp; pi < np; pi += NW) {
       const cplx pp = T.p[pi], aux = T.aux[pi], aux2 = T.aux2[pi];
       cplx series[ZL][UNC_MAX_NACC];
       cplx acc[ZL], fin[ZL];
@@ -1113,34 +1273,37 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       for (int k = 0; k < ZL; ++k) { acc[k] = mk(0.0, 0.0); fin[k] = mk(0.0, 0.0); }
       int seg = 0;
       int next_b = N;
-      for (int base = 0; base < NA; base += 32) {
+      // Wynn only uses the areas before the first non-finite one (integration.f90:140-160) and
+      // driver.f90:209 only asks whether SOME area is finite and non-zero.  Once that is settled
+      // for every z of the warp (dead: a non-finite area seen; anyf: a finite non-zero one seen)
+      // the remaining, ever more expensive, overflowing abscissae cannot change the result.
+      const cplx lt_chk = T.lt[pi];
+      const bool lt_ok = is_finite_fastc(lt_chk) && (lt_chk.re != 0.0 || lt_chk.im != 0.0);
+      int dead = 0, anyf = 0;
+      bool done = false;
+      for (int base = 0; base < NA && !done; base += 32) {
         int ok = 1;
         {
           const int idx = base + lane;
-          if (idx < NA) {
-            StageEnt4 e;
-            ok = ap_terms_fast(P, pp, aux, aux2, s_a2[idx], s_wj[idx], lay_mask, eta_max, &e.eta, e.co) ? 1 : 0;
-            if (zuni && ok) {
-              const cbundle S = cexp_bundle(e.eta.re * Dz, e.eta.im * Dz);
-              e.sp = S.ep;
-              e.sm = S.em;
-            } else { e.sp = mk(1.0, 0.0); e.sm = mk(1.0, 0.0); }
-            stage[lane] = e;
-          }
+          if (idx < NA)
+            ok = ap_terms_stage(P, pp, aux, aux2, s_a2[idx], s_wj[idx], lay_mask, eta_max, zuni, Dz,
+                                &stage[lane]);
           okv[lane] = ok;
         }
         const bool all_ok = __all_sync(0xffffffffu, ok);
         __syncwarp();
+        PROF_ADD(2);
         const int cnt = min(32, NA - base);
         int j = 0;
         while (j < cnt) {
           const int jend = min(cnt, next_b - base);
           if (all_ok && zuni) {
             // hot loop: one exp+sincos for slot 0, complex-multiply recurrence for slots 1..3
-            for (; j < jend; ++j) {
-              const StageEnt4 &e = stage[j];
-              eval4_recur(e, e.co[myL[0]], e.co[myL[1]], e.co[myL[2]], e.co[myL[3]], myz[0], acc);
-            }
+#ifndef UNC_SKIP_HOT
+            if (same_layer) hot_run_same(stage, j, jend, myz[0], myL[0], acc);
+            else hot_run_mixed(stage, j, jend, myz[0], Lpack, acc);
+#endif
+            j = jend;
           } else {
             for (; j < jend; ++j) {
               if (okv[j]) {
@@ -1158,7 +1321,33 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
               }
             }
           }
-          if (base + j == next_b && next_b < NA) {
+          const bool seg_end = (base + j == next_b && next_b < NA);
+          if (seg >= 1 && lt_ok && (seg_end || !all_ok)) {
+            // at an interval end: record its fate; inside an interval that already went
+            // non-finite for everybody (only looked at after chunks with literal nodes): stop
+            int cur_bad = 0;
+#pragma unroll
+            for (int k = 0; k < ZL; ++k) {
+              const bool f = is_finite_fastc(acc[k]);
+              if (!f) cur_bad |= 1 << k;
+              if (seg_end && f && (acc[k].re != 0.0 || acc[k].im != 0.0)) anyf |= 1 << k;
+            }
+            if (seg_end) dead |= cur_bad;
+            const int settled = (dead | cur_bad) & anyf;
+            if (__all_sync(0xffffffffu, settled == (1 << ZL) - 1)) {
+              const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+              for (int k = 0; k < ZL; ++k) {
+                if (seg_end) series[k][seg - 1] = acc[k];
+                for (int jj = seg_end ? seg : seg - 1; jj < nacc; ++jj) series[k][jj] = mk(nanv, nanv);
+                acc[k] = mk(nanv, nanv);
+              }
+              seg = nacc;   // the final store below rewrites series[nacc-1] with NaN
+              done = true;
+              break;
+            }
+          }
+          if (seg_end) {
 #pragma unroll
             for (int k = 0; k < ZL; ++k) {
               if (seg == 0) fin[k] = acc[k]; else series[k][seg - 1] = acc[k];
@@ -1169,6 +1358,7 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
           }
         }
         __syncwarp();
+        PROF_ADD(3);
       }
 #pragma unroll
       for (int k = 0; k < ZL; ++k) { if (seg == 0) fin[k] = acc[k]; else series[k][seg - 1] = acc[k]; }
@@ -1179,38 +1369,46 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
         bool any = false;
         for (int j = 0; j < nacc; ++j) {
           cplx a = series[k][j];
-          a = is_finite_c(a) ? a * lt : mk(nan, nan);
+          const bool fin_a = is_finite_fastc(a);
+          a = fin_a ? a * lt : mk(nan, nan);
           series[k][j] = a;
-          if (cabs_d(a) > 0.0) any = true;  // driver.f90:209
+          if (fin_a && (a.re != 0.0 || a.im != 0.0)) any = true;  // abs(GLarea) > 0, driver.f90:209
         }
         cplx infint = mk(0.0, 0.0);
+#ifdef UNC_SKIP_WYNN
+        if (any) infint = series[k][0];
+#else
         if (any) infint = wynn_any(series[k], nacc);
+#endif
         else stale |= 1 << k;
         cplx f = fin[k];
-        f = is_finite_c(f) ? f * lt : mk(nan, nan);
+        f = is_finite_fastc(f) ? f * lt : mk(nan, nan);
         tot[(size_t)pi * ZB + 32 * k + lane] = f + infint;   // totlap, driver.f90:216
       }
+      PROF_ADD(4);
     }
 #pragma unroll
     for (int k = 0; k < ZL; ++k) if (stale & (1 << k)) atomicOr(&s_flag[32 * k + lane], 1);
     __syncthreads();   // totlap (global, this CTA's slot) and flags complete
+    PROF_ADD(5);
 
-    // ---- phase C: de Hoog ---------------------------------------------------------
-    cplx *scr = s_scr + (size_t)warp * 3 * np;
-    for (int job = warp; job < 2 * nzv; job += UNC_WARPS) {
-      const int zi = job >> 1, deriv = job & 1;
-      double v = dehoog_warp(P, tot + zi, ZB, deriv ? T.p : nullptr, tD, tee, scr, scr + np,
-                             scr + 2 * np, lane);
-      if (lane == 0) {
-        const long long o = col * (long long)J.nz + z0 + zi;
-        if (deriv) J.ds[o] = v * tD;  // driver.f90:228
-        else {
-          J.s[o] = v;
-          if (J.flags) J.flags[o] = s_flag[zi];
-        }
+    // ---- phase C: de Hoog, one inversion per thread ---------------------------------
+    for (int job = tid; job < 2 * nzv; job += NW * 32) {
+      const int deriv = job >= nzv ? 1 : 0;
+      const int zi = job - deriv * nzv;
+#ifdef UNC_SKIP_DEHOOG
+      double v = tot[zi].re;
+#else
+      double v = dehoog_lane(P, tot + zi, ZB, deriv ? T.p : nullptr, tD, tee);
+#endif
+      const long long o = col * (long long)J.nz + z0 + zi;
+      if (deriv) J.ds[o] = v * tD;  // driver.f90:228
+      else {
+        J.s[o] = v;
+        if (J.flags) J.flags[o] = s_flag[zi];
       }
-      __syncwarp();
     }
+    PROF_ADD(6);
   }
 }
 
