@@ -101,12 +101,13 @@ def test_small_radius_columns_overflow_flow_matches_oracle(c5a):
     sg, dg, fg = g["s"][it][:, ir], g["ds"][it][:, ir], g["fl"][it][:, ir]
     assert np.array_equal(fo, fg)
     assert np.array_equal(np.isnan(so), np.isnan(sg))
-    sent = np.abs(so) > 1e4          # sentinel-dominated: -999999.9 passed through de Hoog
-    assert sent.any()
-    ok = np.isfinite(so)
-    rel = np.abs(sg[ok] - so[ok]) / np.maximum(np.abs(so[ok]), 1e-300)
-    assert np.median(rel) < 1e-11
-    assert (rel < 1e-6).mean() > 0.97
+    # the overflow regime is really exercised: at these radii a/sqrt(kappa) exceeds 710
+    assert g["p"]["j0z"][-1] / g["rD"][0] / np.sqrt(g["p"]["kappa"]) > 1000.0
+    args = (g["tD"][it], g["sv"][it], g["rD"][ir], g["zD"], g["lay"])
+    so2, do2, sps, spd = oracle_with_noise(po, args, nsamples=3)
+    keep = fo == 0
+    mask = lambda a: np.where(keep, a, 0.0)   # noqa: E731  (flagged points: documented deviation)
+    check_parity(mask(sg), mask(dg), mask(so2), mask(do2), sps, spd, what="C5a small radii")
 
 
 def test_grid4_equals_grid2_kernel_bitwise_semantics(c5a):
