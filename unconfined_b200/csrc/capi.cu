@@ -349,9 +349,10 @@ int launch_grid4_nw(int dev, const unc::DevParams &P, const unc::Job &J, cudaStr
   const int grid = (int)std::min<long long>(nitems, (long long)c.sm_count * occ);
   int rc = c.scratch.ensure((size_t)grid * P.np * 128 * sizeof(unc::cplx));
   if (rc) return rc;
+  const bool fresh_counter = c.counter.ptr == nullptr;
   rc = c.counter.ensure(256);
   if (rc) return rc;
-  CK(cudaMemsetAsync(c.counter.ptr, 0, 4, st));
+  if (fresh_counter) CK(cudaMemsetAsync(c.counter.ptr, 0, 256, st));   // the kernel re-arms it itself
   unc::lh_grid4_kernel<NW><<<grid, NW * 32, smem, st>>>(P, J, (unc::cplx *)c.scratch.ptr,
                                                          (unsigned int *)c.counter.ptr);
   g_launches++;

@@ -1154,7 +1154,19 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
     }
     __syncthreads();
     const long long item = (unsigned int)s_misc[3];
-    if (item >= nitems) break;
+    if (item >= nitems) {
+      // the last CTA to run dry re-arms both counters, so every launch (and every profiler
+      // replay of a launch) starts from zero without a host-side memset
+      if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(g_counter + 1, 1u) == gridDim.x - 1) {
+          g_counter[0] = 0u;
+          g_counter[1] = 0u;
+          __threadfence();
+        }
+      }
+      break;
+    }
     const long long col = item / nzb;
     const int z0 = (int)(item % nzb) * ZB;
     const int nzv = min(ZB, J.nz - z0);
