@@ -42,10 +42,10 @@ def c5_deck():
                 time_type=1, time_par=[0.0, 1.0])
 
 
-def c5a_grid(rank=0, nr=1024, nz=128, nt=8, rmin=1.0):
+def c5a_grid(rank=0, nr=1024, nz=128, nt=8, rmin=1.0, zfrac=1.0):
     d = c5_deck()
     r = np.linspace(rmin, 500.0, nr)
-    z = np.linspace(0.0, d["b"], nz)
+    z = np.linspace(0.0, d["b"] * zfrac, nz)
     t = 10.0 ** (np.linspace(0.0, 7.0, nt) + rank / 8.0)
     return d, t, r, z
 
@@ -186,7 +186,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    d, t, r, z = c5a_grid(rank, args.nr, args.nz, args.nt, args.rmin)
+    d, t, r, z = c5a_grid(rank, args.nr, args.nz, args.nt, args.rmin, args.zfrac)
     p, tD, sv, rD, zD, lay = derive(d, t, r, z, ub)
     prm = ub.Params(p)
     nt, nr, nz = len(tD), len(rD), len(zD)
@@ -326,6 +326,7 @@ def main():
     ap.add_argument("--nz", type=int, default=128)
     ap.add_argument("--nt", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--zfrac", type=float, default=1.0, help="(experiments only) top of the z grid as a fraction of b")
     ap.add_argument("--rmin", type=float, default=1.0, help="(experiments only) smallest radius of the grid")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

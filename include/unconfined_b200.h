@@ -34,7 +34,7 @@ extern "C" {
 
 #define UNC_OK 0
 #define UNC_ERR_BAD_ARG (-1)     /* invalid size / NULL pointer / parameter out of range */
-#define UNC_ERR_UNSUPPORTED (-2) /* model 6 (Mishra-Neuman), or a table limit exceeded */
+#define UNC_ERR_UNSUPPORTED (-2) /* model 6 with MNtype 0/2 (ARB / finite differences), or a table limit exceeded */
 #define UNC_ERR_NO_DEVICE (-3)   /* no usable CUDA device */
 #define UNC_ERR_CUDA (-4)        /* CUDA runtime failure, see unc_last_error() */
 #define UNC_ERR_IO (-5)          /* deck reader: cannot open / parse */
@@ -47,7 +47,7 @@ extern "C" {
 /* Flattened types.f90 parameter structs (invLaplace :31, invHankel :88, GaussLobatto :98,
  * TanhSinh :117, well :131, formation :145, solution :174).  Fortran: type, bind(C). */
 typedef struct unc_params {
-  int32_t model;        /* s%model 0..5 (types.f90:185); 6 -> UNC_ERR_UNSUPPORTED */
+  int32_t model;        /* s%model 0..5 (types.f90:185); 6 only with mn_type = 1 (below) */
   int32_t M;            /* l%M; np = 2M+1 (driver.f90:79) */
   double alpha;         /* l%alpha (types.f90:39) */
   double tol;           /* l%tol */
@@ -68,7 +68,17 @@ typedef struct unc_params {
   double beta;          /* f%beta -- the DIMENSIONAL beta (laplace_hankel_solutions.f90:86) */
   double lD, dD, bD, rDw; /* w%lD, w%dD, w%bD, w%rDw (driver_io.f90:544-547) */
   double l, d, Ss, rDwobs, sF; /* model 2 only: w%l, w%d, f%Ss, s%rDwobs, s%sF
-                                  (laplace_hankel_solutions.f90:248-251) */
+                                  (laplace_hankel_solutions.f90:248-251); Ss also model 6 */
+  /* model 6, Mishra-Neuman: only s%MNtype = 1, the closed-form double-precision "Malama
+   * finiteness" variant mishraNeumanMalama (laplace_hankel_solutions.f90:404-442), is
+   * supported; MNtype 0 (ARB quad precision) and 2 (finite differences) return
+   * UNC_ERR_UNSUPPORTED.  Ignored for models 0..5. */
+  int32_t mn_type;      /* s%MNtype (types.f90:181) */
+  int32_t mn_reserved;  /* padding, set to 0 */
+  double mn_ak;         /* f%ak, conductivity sorptive number [1/L] (driver_io.f90:159) */
+  double mn_psia, mn_psik; /* f%psia, f%psik [L] */
+  double mn_b;          /* f%b, initial saturated thickness [L] */
+  double mn_Sy;         /* f%Sy */
 } unc_params;
 
 /* One call = driver.f90:100-231 for the whole (t, r, z) grid.

@@ -145,4 +145,7 @@ def params_dict(d):
             "l", "d", "Ss", "rDwobs", "sF")
     out = {k: d[k] for k in keys}
     out["tee_mult"] = 2.0     # driver.f90:54
+    # model 6 (laplace_hankel_solutions.f90:404-442 reads f%ak, f%b, f%psia, f%psik, f%Sy, f%Ss)
+    out.update(mn_type=d["MNtype"], mn_ak=d["ak"], mn_psia=d["psia"], mn_psik=d["psik"],
+               mn_b=d["b"], mn_Sy=d["Sy"])
     return out

@@ -36,6 +36,8 @@ struct params {
   double kappa, alphaD, beta;
   double lD, dD, bD, rDw;
   double l, d, Ss, rDwobs, sF;
+  int32_t mn_type, mn_reserved;
+  double mn_ak, mn_psia, mn_psik, mn_b, mn_Sy;
 };
 
 template <class T> struct consts {
@@ -571,6 +573,26 @@ void lap_hank_soln(T a, T rD, const std::vector<cx<T>> &p, const T *zD, const in
       for (int z = 0; z < nz; ++z) zd[z] = (double)zD[z];
       hantushstorage((double)a, zd.data(), zLay, nz, pd, prm, out);
       for (size_t i = 0; i < out.size(); ++i) fp[i] = cx<T>(out[i].re, out[i].im);
+    }
+  } else if (model == 6) {
+    // laplace_hankel_solutions.f90:404-442  mishraNeumanMalama (MNtype 1; :107-110)
+    const T beta0 = T(prm.mn_ak) * T(prm.mn_b);
+    const T phiDa = T(prm.mn_psia) / T(prm.mn_b);
+    const T phiDk = T(prm.mn_psik) / T(prm.mn_b);
+    const T vartheta = beta0 * T(prm.mn_Sy) / (T(prm.Ss) * T(prm.mn_b)) * std::exp(-beta0 * (phiDa - phiDk));
+    const T u0 = beta0 / T(2);
+    for (int k = 0; k < np; ++k) {
+      cx<T> eta1 = csqrt((p[k] * vartheta + a * a) / T(prm.kappa));
+      cx<T> q = eta1 / u0;
+      cx<T> v = csqrt(T(1) + q * q);
+      cx<T> u = u0 * (T(1) - v);
+      cx<T> etasq = (p[k] + a * a) / T(prm.kappa);
+      cx<T> eta = csqrt(etasq);
+      cx<T> Delta0 = eta * csinh(eta) - u * ccosh(eta);
+      cx<T> pre = T(2) / (T(prm.kappa) * etasq);
+      cx<T> ud = u / Delta0;
+      for (int z = 0; z < nz; ++z)
+        fp[(size_t)k * nz + z] = pre * (T(1) + ud * ccosh(eta * zD[z]));
     }
   } else {
     // models 3..5, laplace_hankel_solutions.f90:64-93

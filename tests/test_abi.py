@@ -29,8 +29,9 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    # 2 int32, 3 double, 2 int32, ptr, 6 int32, 2 ptr, 12 double
-    assert C.sizeof(ub.UncParams) == 8 + 24 + 8 + 8 + 24 + 16 + 96
+    # 2 int32, 3 double, 2 int32, ptr, 6 int32, 2 ptr, 12 double, 2 int32, 5 double
+    assert C.sizeof(ub.UncParams) == 8 + 24 + 8 + 8 + 24 + 16 + 96 + 8 + 40
+    assert C.sizeof(ub.UncParams) == C.sizeof(oracle.OrcParams)
 
 
 def test_host_tables_bitwise_equal_oracle():
@@ -50,10 +51,12 @@ def test_no_cpu_fallback_and_argument_validation():
             ub.eval_grid(prm, d["tD"], d["sv"], d["rD"], d["zD"], d["zLay"])
         assert e.value.code == -3 and "no CPU fallback" in str(e.value)
     # parameter validation happens before any device work
-    bad = dict(pd, model=6)
-    with pytest.raises(ub.UncError) as e:
-        ub.eval_grid(ub.Params(bad), d["tD"], d["sv"], d["rD"], d["zD"], d["zLay"])
-    assert e.value.code in (-2, -3)
+    # model 6: only MNtype 1 (closed-form Malama variant) exists; 0 (ARB) and 2 (FD) are refused
+    for mn in (0, 2):
+        bad = dict(pd, model=6, mn_type=mn, mn_ak=0.5, mn_b=20.0, mn_psia=0.02, mn_psik=0.02, mn_Sy=0.3)
+        with pytest.raises(ub.UncError) as e:
+            ub.eval_grid(ub.Params(bad), d["tD"], d["sv"], d["rD"], d["zD"], d["zLay"])
+        assert e.value.code == -2 and "MNtype" in str(e.value)
     # empty inputs succeed trivially
     s, ds = ub.eval_points(prm, [], [], [], [], [])
     assert s.size == 0

@@ -16,7 +16,7 @@ def test_all_shipped_decks_parse():
     for f in sorted(os.listdir(CFG)):
         if f.endswith("-input.dat") or f.endswith(".in"):
             d = deck.read_deck(os.path.join(CFG, f))
-            assert 0 <= d["model"] <= 5 and len(d["tD"]) >= 1 and len(d["j0z"]) == max(d["j0s"]) + d["gl_nacc"] + 1
+            assert 0 <= d["model"] <= 6 and len(d["tD"]) >= 1 and len(d["j0z"]) == max(d["j0s"]) + d["gl_nacc"] + 1
             n += 1
     assert n >= 10
 

@@ -21,8 +21,8 @@ HC_DIR = os.path.join(ROOT, "tests", "hostcheck")
 def hc():
     so = os.path.join(HC_DIR, "libhostcheck.so")
     src = os.path.join(HC_DIR, "hostcheck.cu")
-    dep = os.path.join(ROOT, "unconfined_b200", "csrc", "fast.cuh")
-    if not os.path.exists(so) or max(os.path.getmtime(src), os.path.getmtime(dep)) > os.path.getmtime(so):
+    deps = [os.path.join(ROOT, "unconfined_b200", "csrc", f) for f in ("fast.cuh", "wynn.cuh", "cmath.cuh", "params.cuh")]
+    if not os.path.exists(so) or max([os.path.getmtime(src)] + [os.path.getmtime(f) for f in deps]) > os.path.getmtime(so):
         subprocess.run(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
                         "-Xcompiler", "-fPIC", "-shared", "-o", so, src], check=True, capture_output=True)
     return C.CDLL(so)
@@ -201,7 +201,43 @@ def test_device_wynn_matches_oracle_including_edge_semantics(hc):
     for s in cases:
         want, info = oracle.wynn(s)
         n_cancel += info == 3
-        for which in (0, 1, 2):
+        for which in (0, 1, 2, 3):
             got = _hc_wynn(hc, s, which)
             assert abs(got - want) <= 1e-12 * max(abs(want), 1e-300) + 1e-300, (which, info, s, got, want)
     assert n_cancel >= 5        # the early-exit branch was really exercised
+
+
+def test_model6_fast_path_matches_literal_formula(hc):
+    """mishraNeumanMalama (laplace_hankel_solutions.f90:404-442) closed form vs the formula
+    as written, in 40-digit arithmetic.  u = u0(1 - sqrt(1 + (eta1/u0)^2)) cancels in double
+    for |eta1| << u0 (in the reference too): that part of the error is bounded separately."""
+    mp.mp.dps = 40
+    d, pd = load_deck("mishra-neuman-malama.in")
+    assert pd["model"] == 6 and pd["mn_type"] == 1
+    po = oracle.Params(pd)
+    beta0 = pd["mn_ak"] * pd["mn_b"]
+    vartheta = beta0 * pd["mn_Sy"] / (pd["Ss"] * pd["mn_b"]) * math.exp(-beta0 * (pd["mn_psia"] - pd["mn_psik"]) / pd["mn_b"])
+    u0 = beta0 / 2
+    hc.hc_set_mn(C.c_double(vartheta), C.c_double(u0))
+    zD = np.array([0.0, 0.2, 0.77, 1.0]); lay = np.array([1, 1, 1, 1])
+    worst = 0.0
+    for tD in (0.05, 3.0, 1e3, 1e7):
+        pv = oracle.pvalues(po, 2 * tD)
+        for a in (1e-3, 0.03, 0.7, 5.0, 40.0, 150.0):
+            for k in (0, 1, len(pv) // 2, len(pv) - 1):
+                ok, got, eta = fast_soln(hc, pd, a, complex(pv[k]), zD, lay)
+                assert ok
+                p = mp.mpc(pv[k].real, pv[k].imag)
+                eta1 = mp.sqrt((p * vartheta + a * a) / pd["kappa"])
+                v = mp.sqrt(1 + (eta1 / u0) ** 2)
+                u = u0 * (1 - v)
+                etasq = (p + a * a) / pd["kappa"]
+                et = mp.sqrt(etasq)
+                D0 = et * mp.sinh(et) - u * mp.cosh(et)
+                for i, z in enumerate(zD):
+                    tr = 2 / (pd["kappa"] * etasq) * (1 + u / D0 * mp.cosh(et * z))
+                    cancel = 4 * 2.2e-16 * u0 * abs(2 / (pd["kappa"] * etasq) * mp.cosh(et * z) / D0)
+                    err = abs(got[i] - complex(tr))
+                    assert err <= 2e-13 * abs(tr) + float(cancel), (tD, a, k, z, got[i], complex(tr))
+                    worst = max(worst, err / abs(tr))
+    assert worst < 1e-6

@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 
 DECKS = ["theis-input.dat", "hantush-input.dat", "cape-cod-neuman74.in", "cape-cod-moench.in",
          "malama-partpen-input.dat", "malama-fullpen-input.dat", "hantush-storage-input.dat",
-         "hantush-fullpen-test.in", "theis-contours-input.dat", "hantush-contours-input.dat"]
+         "hantush-fullpen-test.in", "theis-contours-input.dat", "hantush-contours-input.dat",
+         "mishra-neuman-malama.in"]
 
 
 @pytest.fixture(autouse=True)
@@ -65,7 +66,8 @@ def test_baseline_configs_strict_1e9_on_drawdown():
 
 
 def test_against_committed_golden_fixtures():
-    for name in ("hantush-input.dat", "cape-cod-neuman74.in", "cape-cod-moench.in", "hantush-storage-input.dat"):
+    for name in ("hantush-input.dat", "cape-cod-neuman74.in", "cape-cod-moench.in", "hantush-storage-input.dat",
+                 "mishra-neuman-malama.in"):
         g = np.load(os.path.join(ROOT, "tests", "golden", "oracle_" + name.replace(".", "_") + ".npz"))
         d, pd = load_deck(name)
         sg, dg = ub.eval_grid(ub.Params(pd), g["tD"], g["sv"], g["rD"], g["zD"], g["zLay"],

@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 from oracle import oracle, deck  # noqa: E402
 
 DECKS = ["theis-input.dat", "hantush-input.dat", "cape-cod-neuman74.in", "cape-cod-moench.in",
-         "hantush-storage-input.dat", "hantush-contours-input.dat"]
+         "hantush-storage-input.dat", "hantush-contours-input.dat", "mishra-neuman-malama.in"]
 
 for name in DECKS:
     d = deck.read_deck(os.path.join(ROOT, "configs", name))

@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) hot(const StageEnt4 *g_stage, d
   cplx acc[4];
   for (int k = 0; k < 4; ++k) acc[k] = mk(0, 0);
   const double z0 = 0.001 * lane;
+  const int l0 = reps < 0 ? 1 : 0, l1 = reps < -1 ? 1 : 0, l2 = reps < -2 ? 1 : 0, l3 = (lane >= 29 && reps > 0) ? 1 : 0;
+  (void)l0; (void)l1; (void)l2; (void)l3;
   for (int r = 0; r < reps; ++r) {
 #if MODE >= 1
     {
@@ -43,8 +45,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) hot(const StageEnt4 *g_stage, d
 #pragma unroll kUnroll
     for (int j = 0; j < 32; ++j) {
       const StageEnt4 &e = stage[j];
+#ifdef MIXED
+      eval4_recur(e, e.co[l0], e.co[l1], e.co[l2], e.co[l3], z0, acc);
+#else
       const Coef c0 = e.co[0];
       eval4_recur(e, c0, c0, c0, c0, z0, acc);
+#endif
     }
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc[0].re + acc[1].im + acc[2].re + acc[3].im;

@@ -16,7 +16,7 @@ ub.eval_grid(prm, tD, sv, rD, zD, lay)
 dt = time.perf_counter() - t0
 ub.lib().unc_debug_profile(out, 0)
 v = np.array(out[:7], float)
-names = ['item fetch+sync', 'prologue', 'ap_terms(stage)', 'hot loop', 'wynn/phaseB', 'barrier wait', 'de Hoog']
+names = ['barrier wait+fetch', 'prologue', 'ap_terms(stage)', 'hot loop', 'wynn/phaseB', 'pool exit', 'de Hoog']
 print('wall %.1f ms for %d points -> %.3g points/s' % (dt * 1e3, len(tD) * len(rD) * len(zD), len(tD) * len(rD) * len(zD) / dt))
 for n, x in zip(names, v):
     print('%-18s %6.2f%%' % (n, 100 * x / v.sum()))

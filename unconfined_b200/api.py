@@ -35,6 +35,9 @@ class UncParams(C.Structure):
         ("lD", C.c_double), ("dD", C.c_double), ("bD", C.c_double), ("rDw", C.c_double),
         ("l", C.c_double), ("d", C.c_double), ("Ss", C.c_double), ("rDwobs", C.c_double),
         ("sF", C.c_double),
+        ("mn_type", C.c_int32), ("mn_reserved", C.c_int32),
+        ("mn_ak", C.c_double), ("mn_psia", C.c_double), ("mn_psik", C.c_double),
+        ("mn_b", C.c_double), ("mn_Sy", C.c_double),
     ]
 
 
@@ -80,6 +83,8 @@ class Params:
         for k in ("model", "M", "alpha", "tol", "ts_k", "ts_R", "gl_nacc", "gl_ord", "kappa",
                   "alphaD", "beta", "lD", "dD", "bD", "rDw", "l", "d", "Ss", "rDwobs", "sF"):
             setattr(s, k, d[k])
+        for k in ("mn_type", "mn_ak", "mn_psia", "mn_psik", "mn_b", "mn_Sy"):
+            setattr(s, k, d.get(k, 0))
         s.tee_mult = d.get("tee_mult", 2.0)
         s.time_type = d.get("time_type", 1)
         s.n_time_par = len(self._tp)

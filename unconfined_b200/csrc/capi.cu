@@ -133,8 +133,15 @@ struct HostPlan {
 
 int make_plan(const unc_params *prm, HostPlan &hp) {
   if (!prm) return fail(UNC_ERR_BAD_ARG, "prm is NULL");
-  if (prm->model == 6) return fail(UNC_ERR_UNSUPPORTED, "model 6 (Mishra-Neuman) is out of scope");
   if (prm->model < 0 || prm->model > 6) return fail(UNC_ERR_BAD_ARG, "invalid model %d", prm->model);
+  if (prm->model == 6) {
+    if (prm->mn_type == 0 || prm->mn_type == 2)
+      return fail(UNC_ERR_UNSUPPORTED, "model 6 MNtype %d (ARB quad precision / finite-difference "
+                  "Mishra-Neuman) is out of scope; only MNtype 1 is supported", prm->mn_type);
+    if (prm->mn_type != 1) return fail(UNC_ERR_BAD_ARG, "invalid MNtype %d (driver_io.f90:272)", prm->mn_type);
+    if (!(prm->mn_b > 0.0) || !(prm->Ss > 0.0) || !(prm->mn_ak > 0.0))
+      return fail(UNC_ERR_BAD_ARG, "model 6 needs mn_b, Ss, mn_ak > 0");
+  }
   if (prm->M < 2) return fail(UNC_ERR_BAD_ARG, "de Hoog M must be >= 2 (driver_io.f90:308)");
   if (prm->M > 31) return fail(UNC_ERR_UNSUPPORTED, "de Hoog M > 31 not supported (2M+1 <= 63)");
   if (prm->ts_R < 1 || prm->ts_k - prm->ts_R < 2)
@@ -184,6 +191,14 @@ int make_plan(const unc_params *prm, HostPlan &hp) {
   P.lD = prm->lD; P.dD = prm->dD; P.bD = prm->bD; P.rDw = prm->rDw;
   P.lD1 = 1.0 - prm->lD;            // laplace_hankel_solutions.f90:159-160
   P.dD1 = 1.0 - prm->dD;
+  if (prm->model == 6) {
+    // laplace_hankel_solutions.f90:424-431 (run constants of mishraNeumanMalama)
+    const double beta0 = prm->mn_ak * prm->mn_b;
+    const double phiDa = prm->mn_psia / prm->mn_b;
+    const double phiDk = prm->mn_psik / prm->mn_b;
+    P.mn_vartheta = beta0 * prm->mn_Sy / (prm->Ss * prm->mn_b) * std::exp(-beta0 * (phiDa - phiDk));
+    P.mn_u0 = beta0 / 2.0;
+  }
   if (prm->model == 2) {
     const double PI = 4.0 * std::atan(1.0);
     P.CDw = prm->rDw * prm->rDw / (2.0 * (prm->l - prm->d) * prm->Ss);   // :248
@@ -347,7 +362,7 @@ int launch_grid4_nw(int dev, const unc::DevParams &P, const unc::Job &J, cudaStr
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, unc::lh_grid4_kernel<NW>, NW * 32, smem));
   if (occ < 1) occ = 1;
   const int grid = (int)std::min<long long>(nitems, (long long)c.sm_count * occ);
-  int rc = c.scratch.ensure((size_t)grid * P.np * 128 * sizeof(unc::cplx));
+  int rc = c.scratch.ensure((size_t)grid * 2 * P.np * 128 * sizeof(unc::cplx));   // two totlap slots per CTA
   if (rc) return rc;
   const bool fresh_counter = c.counter.ptr == nullptr;
   rc = c.counter.ensure(256);
@@ -361,9 +376,11 @@ int launch_grid4_nw(int dev, const unc::DevParams &P, const unc::Job &J, cudaStr
 }
 
 int launch_grid4(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
-  const char *nw = getenv("UNC_GRID4_WARPS");
-  if (nw && atoi(nw) == 7) return launch_grid4_nw<7>(dev, P, J, st);
+#ifdef UNC_GRID4_NW
+  return launch_grid4_nw<UNC_GRID4_NW>(dev, P, J, st);   // experiments (tools/run_variants.sh)
+#else
   return launch_grid4_nw<8>(dev, P, J, st);
+#endif
 }
 
 int launch_grid(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
@@ -528,14 +545,14 @@ int run_shard(const unc_params *prm, const HostJob &hj, Shard &sh) {
 
 int run_host(const unc_params *prm, const HostJob &hj, int ngpu) {
   std::lock_guard<std::mutex> lk(g_mutex);
-  const int avail = device_count();
-  if (avail <= 0) return fail(UNC_ERR_NO_DEVICE, "no CUDA device available (there is no CPU fallback)");
   {
-    HostPlan probe;
+    HostPlan probe;   // parameter validation is host-only and comes before any device work
     int rc = make_plan(prm, probe);
     if (rc) return rc;
   }
   if (ngpu < 0) return fail(UNC_ERR_BAD_ARG, "ngpu < 0");
+  const int avail = device_count();
+  if (avail <= 0) return fail(UNC_ERR_NO_DEVICE, "no CUDA device available (there is no CPU fallback)");
   int use = ngpu == 0 ? avail : std::min(ngpu, avail);
   if (hj.ncol < use) use = (int)std::max<long long>(1, hj.ncol);
   if (use == 1) {

@@ -18,7 +18,8 @@
 
 namespace unc {
 
-struct cplx {
+// 16-byte alignment: shared/local/global accesses of a cplx are single 128-bit transactions
+struct __align__(16) cplx {
   double re, im;
 };
 

@@ -37,6 +37,7 @@ namespace unc {
 __host__ __device__ __forceinline__ double fast_eta_max(const DevParams &P, int lay_mask, double zabs_max) {
   double m = 1.0;
   if (P.model == 3 || P.model == 5 || (lay_mask & 4)) m = 1.0 + P.dD;
+  if (P.model == 6) m = 1.03;   // Delta0 = eta sinh(eta) - u cosh(eta): headroom for the factors eta, u
   if (zabs_max > m) m = zabs_max;
   return UNC_FAST_EXP_MAX / m;
 }
@@ -258,6 +259,24 @@ __host__ __device__ __forceinline__ bool ap_terms_fast(const DevParams &P, cplx 
   *eta_out = eta;
   if (!(eta.re <= eta_max && eta.im <= 2.0e5)) return false;  // overflow bound; sincos_q range
   const cbundle E1 = cexp_bundle(eta.re, eta.im);
+  if (model == 6) {
+    // mishraNeumanMalama (laplace_hankel_solutions.f90:404-442):
+    //   2/(kappa eta^2) (1 + u/Delta0 cosh(eta z)),  Delta0 = eta sinh(eta) - u cosh(eta),
+    //   u = u0 (1 - sqrt(1 + (eta1/u0)^2)),  eta1 = sqrt((p vartheta + a^2)/kappa).
+    // u keeps the reference's form u0 (1 - v): for |eta1| << u0 its value is dominated by the
+    // rounding of 1 + (eta1/u0)^2 and of the square root, which are the same IEEE operations
+    // here, so the (large) cancellation noise of the reference is tracked, not "fixed".
+    const cplx e1sq = cscalef(mk(fma(p.re, P.mn_vartheta, a2), p.im * P.mn_vartheta), 1.0 / P.kappa);
+    const double iu02 = 1.0 / (P.mn_u0 * P.mn_u0);
+    const cplx v = csqrt_pos(mk(1.0 + e1sq.re * iu02, e1sq.im * iu02));
+    const cplx u = cscalef(mk(1.0 - v.re, -v.im), P.mn_u0);
+    const cplx D0 = csubf(cmulf(eta, E1.sh), cmulf(u, E1.ch));
+    const cplx th = cscalef(crecipf(pa), 2.0 * w);       // 2/(kappa eta^2) = 2/(p + a^2)
+    const cplx g = cscalef(cmulf(th, cdivf(u, D0)), 0.5);
+#pragma unroll
+    for (int L = 0; L < 3; ++L) { co[L].k0 = th; co[L].cp = g; co[L].cm = g; }
+    return true;
+  }
   cplx K0;  // common prefactor of the layer functions, weight folded in
   if (model == 2) K0 = cscalef(cdivf(aux, cmulf(pa, aux2)), w / P.bD);            // uDf/bD :265-266,299
   else K0 = cscalef(crecipf(pa), 2.0 * w / ((model == 4) ? 1.0 : P.bD));          // theis/bD

@@ -268,6 +268,21 @@ __device__ __forceinline__ void soln_literal(const DevParams &P, const PTab &T, 
     return;
   }
   const cplx eta = csqrt_g((p + a2) / P.kappa);
+  if (model == 6) {
+    // laplace_hankel_solutions.f90:404-442  mishraNeumanMalama (MNtype 1)
+    const cplx eta1 = csqrt_g((p * P.mn_vartheta + a2) / P.kappa);
+    const cplx q = eta1 / P.mn_u0;
+    const cplx v = csqrt_g(1.0 + q * q);
+    const cplx u = P.mn_u0 * (1.0 - v);
+    const cplx etasq = (p + a2) / P.kappa;
+    const cplx Delta0 = eta * csinh_g(eta) - u * ccosh_g(eta);
+    const cplx pre = 2.0 / (P.kappa * etasq);
+    const cplx ud = u / Delta0;
+#pragma unroll
+    for (int i = 0; i < ZT; ++i)
+      if (i < nzt) f[i] = pre * (1.0 + ud * ccosh_g(eta * z[i]));
+    return;
+  }
   if (model == 1) {
     cplx dummy;
     hantush_literal<ZT>(P, a2, p, eta, z, lay, nzt, false, f, &dummy, false);
@@ -391,29 +406,53 @@ __device__ __noinline__ double dehoog_warp(const DevParams &P, const cplx *f, in
   return exp(gamma * t) / tee * (A2M / B2M).re;
 }
 
+// Complex quotient for the q-d table: a * conj(b)/|b|^2 with the hardware reciprocal + two
+// Newton steps (<= ~2 ulp) while |b| is far from the over/underflow of |b|^2; otherwise the
+// reference's own Smith division, so zero/huge/tiny divisors keep their Inf/NaN flow.
+__device__ __forceinline__ cplx cdiv_q(cplx a, cplx b) {
+  const double m = fmax(fabs(b.re), fabs(b.im));
+  if (m > 1e-140 && m < 1e140) {
+    const double inv = rcp_fast(fma(b.re, b.re, b.im * b.im));
+    return cmulf(a, mk(b.re * inv, -(b.im * inv)));
+  }
+  return a / b;
+}
+
 // The same inversion done by ONE thread (lane-parallel over inversions): the warp version
 // above keeps 32 lanes on a <=53-entry row and pays ~7000 warp instructions per inversion;
 // with one inversion per lane the q-d table is two thread-local columns updated in place
 // (e(i,r) and q(i,r+1) only read entries at i and i+1 of the previous column).
+// deriv: invert fp*p (driver.f90:228) with p regenerated as in deHoog_pvalues.
 __device__ __noinline__ double dehoog_lane(const DevParams &P, const cplx *f, int fstride,
-                                           const cplx *pmul, double t, double tee) {
+                                           bool deriv, double t, double tee) {
   const int M = P.M, n2 = 2 * M;
+  const double PI = 3.141592653589793;
   cplx q[2 * 31 + 2], e[2 * 31 + 2], d[2 * 31 + 2];
   double mx = -1.0;
   bool anynum = false;
+  const double sigma = P.alpha - P.log_tol / (2.0 * tee);   // invlap.f90:166-170
   for (int i = 0; i <= n2; ++i) {
     cplx v = f[(size_t)i * fstride];
-    if (pmul) v = v * pmul[i];
-    double a = hypot(v.re, v.im);
-    if (!isnan(a)) { anynum = true; mx = fmax(mx, a); }
-    if (isnan(v.re) || isnan(v.im)) v = mk(0.0, 0.0);
+    if (deriv) v = v * mk(sigma, PI * (double)i / tee);
+    // maxval(abs(fp)) > tiny (invlap.f90:69): abs = hypot, which is NaN iff a component is NaN
+    // and none is Inf; the largest |component| decides except in the band [tiny/2, tiny]
+    const bool nn = isnan(v.re) || isnan(v.im);
+    const bool inf = isinf(v.re) || isinf(v.im);
+    if (!(nn && !inf)) { anynum = true; mx = fmax(mx, fmax(fabs(v.re), fabs(v.im))); }
+    if (nn) v = mk(0.0, 0.0);
     d[i] = v;
     e[i] = mk(0.0, 0.0);
   }
-  if (!anynum || !(mx > DBL_MIN)) return 0.0;
-  q[0] = d[1] / (d[0] / 2.0);
-  for (int i = 1; i <= n2 - 1; ++i) q[i] = d[i + 1] / d[i];
-  d[0] = d[0] / 2.0;
+  if (!anynum) return 0.0;
+  if (!(mx > DBL_MIN)) {
+    if (!(mx > 0.5 * DBL_MIN)) return 0.0;
+    double mh = 0.0;
+    for (int i = 0; i <= n2; ++i) mh = fmax(mh, hypot(d[i].re, d[i].im));
+    if (!(mh > DBL_MIN)) return 0.0;
+  }
+  q[0] = cdiv_q(d[1], mk(0.5 * d[0].re, 0.5 * d[0].im));
+  for (int i = 1; i <= n2 - 1; ++i) q[i] = cdiv_q(d[i + 1], d[i]);
+  d[0] = mk(0.5 * d[0].re, 0.5 * d[0].im);
   // rows are processed in register blocks of UB entries so that the thread-local loads of a
   // block are all in flight together (the table lives in L2-backed local memory)
   constexpr int UB = 6;
@@ -452,14 +491,13 @@ __device__ __noinline__ double dehoog_lane(const DevParams &P, const cplx *f, in
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
           if (i0 + u <= mxi) {
-            q[i0 + u] = qn[u] * en[u] / ei;
+            q[i0 + u] = cdiv_q(qn[u] * en[u], ei);
             ei = en[u];
           }
         }
       }
     }
   }
-  const double PI = 3.141592653589793;
   double sn, cs;
   sincos_g((PI * t) / tee, &sn, &cs);
   const cplx zz = mk(cs, sn);
@@ -476,6 +514,21 @@ __device__ __noinline__ double dehoog_lane(const DevParams &P, const cplx *f, in
   cplx B2M = Bm1 + rem * Bm2;
   const double gamma = P.alpha - P.log_tol / (2.0 * tee);
   return exp(gamma * t) / tee * (A2M / B2M).re;
+}
+
+// Wynn-epsilon for the grid kernel.  Measured alternatives (C5a, ms per step): two
+// local-memory columns (wynn_dev) 127.4; epsilon table in registers, anti-diagonal order
+// (wynn_reg<12>, one serial dependency chain) 146; four series in lockstep over local
+// memory 135.4.  UNC_WYNN_REG selects the register variant for experiments.
+__device__ __noinline__ cplx wynn_grid(const cplx *series, int nacc) {
+#ifdef UNC_WYNN_REG
+  if (nacc <= 12) return wynn_reg<12>(series, nacc);
+#endif
+#ifdef UNC_WYNN_BLK
+  return wynn_blk(series, nacc);
+#else
+  return wynn_dev(series, nacc);
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -1026,7 +1079,7 @@ __host__ __device__ inline size_t grid4_smem_bytes(int np, int na_seq, int NW) {
   size_t stage = (size_t)NW * 32 * sizeof(StageEnt4) + (size_t)NW * 32 * sizeof(int);
   size_t scratch = (size_t)NW * 3 * np * sizeof(cplx);
   b += stage > scratch ? stage : scratch;
-  b += 128 * sizeof(int) + 64;
+  b += 2 * 128 * sizeof(int) + 64;
   return (b + 15) & ~(size_t)15;
 }
 
@@ -1059,11 +1112,16 @@ __device__ __forceinline__ void eval4_recur(const StageEnt4 &e, const Coef &c0, 
 // rematerialisation (S2R/R2UR) and extra loads; as a call it gets its own register
 // allocation (the isolated loop runs at 98% of the FP64 pipe, tools/micro/hotloop_bench.cu).
 // acc lives in the caller's local memory only across the call.
+#ifndef UNC_HOT_UNROLL
+#define UNC_HOT_UNROLL 1
+#endif
+constexpr int kHotUnroll = UNC_HOT_UNROLL;
 __device__ __noinline__ void hot_run_same(const StageEnt4 *stage, int j, int jend, double z0, int L,
                                           cplx *acc_io) {
   cplx acc[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) acc[k] = acc_io[k];
+#pragma unroll kHotUnroll
   for (; j < jend; ++j) {
     const StageEnt4 &e = stage[j];
     const Coef c = e.co[L];
@@ -1079,9 +1137,30 @@ __device__ __noinline__ void hot_run_mixed(const StageEnt4 *stage, int j, int je
 #pragma unroll
   for (int k = 0; k < 4; ++k) acc[k] = acc_io[k];
   const int l0 = Lpack & 3, l1 = (Lpack >> 2) & 3, l2 = (Lpack >> 4) & 3, l3 = (Lpack >> 6) & 3;
+#pragma unroll kHotUnroll
   for (; j < jend; ++j) {
     const StageEnt4 &e = stage[j];
     eval4_recur(e, e.co[l0], e.co[l1], e.co[l2], e.co[l3], z0, acc);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc_io[k] = acc[k];
+}
+
+// One slot (KX) with lane-dependent layers, the other three on the common layer L: the usual
+// case of a z-block that straddles a layer boundary (z ascending, so the boundary falls in
+// one slot).  Three broadcast loads for the common coefficients plus three per-lane ones,
+// instead of twelve per-lane loads and four coefficient sets in registers.
+template <int KX>
+__device__ __noinline__ void hot_run_exc(const StageEnt4 *stage, int j, int jend, double z0, int L,
+                                         int Lx, cplx *acc_io) {
+  cplx acc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc[k] = acc_io[k];
+  for (; j < jend; ++j) {
+    const StageEnt4 &e = stage[j];
+    const Coef c = e.co[L];
+    const Coef cx = e.co[Lx];
+    eval4_recur(e, KX == 0 ? cx : c, KX == 1 ? cx : c, KX == 2 ? cx : c, KX == 3 ? cx : c, z0, acc);
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) acc_io[k] = acc[k];
@@ -1140,22 +1219,35 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
     size_t scratch = (size_t)NW * 3 * np * sizeof(cplx);
     sp += stage > scratch ? stage : scratch;
   }
-  int *s_flag = (int *)sp; sp += 128 * sizeof(int);
-  int *s_misc = (int *)sp;  // [0] layer mask, [1] max|z| bits, [2] uniform-z flag, [3..4] item, [5..6] D
-  cplx *tot = g_tot + (size_t)blockIdx.x * np * ZB;  // this CTA's totlap slot [p][z]
+  int *s_flag = (int *)sp; sp += 2 * 128 * sizeof(int);   // stale flags per z, [buffer][z]
+  int *s_misc = (int *)sp;  // [0] layer mask, [1] max|z| bits, [2] uniform-z flag, [3] item, [6..7] D, [8] job counter
+  cplx *tot_base = g_tot + (size_t)blockIdx.x * 2 * np * ZB;  // this CTA's two totlap slots [p][z]
 
+  // Software pipeline over work items: round i runs the np quadrature jobs ("p-jobs") of
+  // item i AND the de Hoog jobs ("D-jobs", 32 inversions each, one per lane) of item i-1 out
+  // of one job pool that the warps drain through a shared-memory counter.  The small D-jobs
+  // come last, so the warps that run out of p-jobs invert the previous item's totlap while
+  // the others finish: no separate de Hoog phase with every warp stalled on its q-d table,
+  // and the end-of-round barrier waits for a D-job at most, not for a p-job.
+  int buf = 0;
+  bool have_prev = false, dry = false;
+  long long prev_col = 0;
+  int prev_z0 = 0, prev_nzv = 0;
+  double prev_tD = 0.0;
   PROF_T0();
   for (;;) {
-    __syncthreads();
+    __syncthreads();   // every job of the previous round is complete
     PROF_ADD(0);
     if (tid == 0) {
-      unsigned int it = atomicAdd(g_counter, 1u);
-      s_misc[3] = (int)it;
+      if (!dry) s_misc[3] = (int)atomicAdd(g_counter, 1u);
+      s_misc[8] = 0;
     }
     __syncthreads();
     const long long item = (unsigned int)s_misc[3];
-    if (item >= nitems) {
-      // the last CTA to run dry re-arms both counters, so every launch (and every profiler
+    const bool have_cur = item < nitems;
+    if (!have_cur) dry = true;
+    if (!have_cur && !have_prev) {
+      // the last CTA to finish re-arms both counters, so every launch (and every profiler
       // replay of a launch) starts from zero without a host-side memset
       if (tid == 0) {
         __threadfence();
@@ -1167,10 +1259,14 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       }
       break;
     }
-    const long long col = item / nzb;
-    const int z0 = (int)(item % nzb) * ZB;
-    const int nzv = min(ZB, J.nz - z0);
+    cplx *tot = tot_base + (size_t)buf * np * ZB;
+    const cplx *tot_prev = tot_base + (size_t)(buf ^ 1) * np * ZB;
+    int *flag_cur = s_flag + buf * 128;
+    const int *flag_prev = s_flag + (buf ^ 1) * 128;
 
+    const long long col = have_cur ? item / nzb : 0;
+    const int z0 = have_cur ? (int)(item % nzb) * ZB : 0;
+    const int nzv = have_cur ? min(ZB, J.nz - z0) : 0;
     const double tD = J.tD[col / J.tdiv];
     const int sv = J.sv[col / J.tdiv];
     const double rD = J.rD[col % J.rmod];
@@ -1189,72 +1285,74 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       mylay[k] = zvalid[k] ? J.zLay[zbase + zi] : 0;
     }
 
-    // ---- prologue -------------------------------------------------------------
-    if (tid < ZB) s_flag[tid] = 0;
-    for (int i = tid; i < np; i += NW * 32) {
-      const double PI = 3.141592653589793;
-      double sigma = P.alpha - P.log_tol / (2.0 * tee);   // invlap.f90:166-170
-      cplx p = mk(sigma, PI * (double)i / tee);
-      T.p[i] = p;
-      T.lt[i] = laptime_dev(P, p);
-      cplx aux = mk(0.0, 0.0), aux2 = mk(0.0, 0.0);
-      if (P.model == 3) {
-        for (int m = 0; m < P.moench_M; ++m) aux = aux + 1.0 / (1.0 + p * (1.0 / P.moench_gamma[m]));
-      } else if (P.model == 2) {
-        cplx xi = P.rDw * csqrt_g(p);
-        cplx K[2];
-        cbesk01_dev(xi, K);
-        aux = 2.0 / (p * P.CDw * K[0] + xi * K[1]);
-        aux2 = p * P.tDb + 1.0;
+    // ---- prologue (tables of the current item) -----------------------------------
+    if (have_cur) {
+      if (tid < ZB) flag_cur[tid] = 0;
+      for (int i = tid; i < np; i += NW * 32) {
+        const double PI = 3.141592653589793;
+        double sigma = P.alpha - P.log_tol / (2.0 * tee);   // invlap.f90:166-170
+        cplx p = mk(sigma, PI * (double)i / tee);
+        T.p[i] = p;
+        T.lt[i] = laptime_dev(P, p);
+        cplx aux = mk(0.0, 0.0), aux2 = mk(0.0, 0.0);
+        if (P.model == 3) {
+          for (int m = 0; m < P.moench_M; ++m) aux = aux + 1.0 / (1.0 + p * (1.0 / P.moench_gamma[m]));
+        } else if (P.model == 2) {
+          cplx xi = P.rDw * csqrt_g(p);
+          cplx K[2];
+          cbesk01_dev(xi, K);
+          aux = 2.0 / (p * P.CDw * K[0] + xi * K[1]);
+          aux2 = p * P.tDb + 1.0;
+        }
+        T.aux[i] = aux;
+        T.aux2[i] = aux2;
       }
-      T.aux[i] = aux;
-      T.aux2[i] = aux2;
-    }
-    for (int idx = tid; idx < na_seq; idx += NW * 32) {
-      double a = 0.0, w = 0.0;
-      if (idx < N) {
-        a = (P.ts_T[idx] * tscale) / 2.0;  // integration.f90:62
-        w = P.ts_wc[idx] * (arg / 2.0);    // driver.f90:135,154 + Richardson (linear in tmp)
-      } else if (idx < NA) {
-        const int node = idx - N;
-        const int j = node / G, m = node - j * G;
-        const double lob = P.j0z[sv + j - 1] / rD;  // driver.f90:188-193
-        const double hib = P.j0z[sv + j] / rD;
-        const double width = hib - lob;
-        a = fma(width, P.gl_x[m], hib + lob) / 2.0;
-        w = P.gl_w[m] * (width / 2.0);
+      for (int idx = tid; idx < na_seq; idx += NW * 32) {
+        double a = 0.0, w = 0.0;
+        if (idx < N) {
+          a = (P.ts_T[idx] * tscale) / 2.0;  // integration.f90:62
+          w = P.ts_wc[idx] * (arg / 2.0);    // driver.f90:135,154 + Richardson (linear in tmp)
+        } else if (idx < NA) {
+          const int node = idx - N;
+          const int j = node / G, m = node - j * G;
+          const double lob = P.j0z[sv + j - 1] / rD;  // driver.f90:188-193
+          const double hib = P.j0z[sv + j] / rD;
+          const double width = hib - lob;
+          a = fma(width, P.gl_x[m], hib + lob) / 2.0;
+          w = P.gl_w[m] * (width / 2.0);
+        }
+        s_a2[idx] = a * a;
+        s_wj[idx] = (w != 0.0) ? w * (a * j0_dev(a * rD)) : 0.0;  // laplace_hankel_solutions.f90:118
       }
-      s_a2[idx] = a * a;
-      s_wj[idx] = (w != 0.0) ? w * (a * j0_dev(a * rD)) : 0.0;  // laplace_hankel_solutions.f90:118
-    }
-    if (warp == 0) {
-      int m = 0;
-      float za = 0.f;
+      if (warp == 0) {
+        int m = 0;
+        float za = 0.f;
 #pragma unroll
-      for (int k = 0; k < ZL; ++k)
-        if (zvalid[k]) { m |= 1 << (mylay[k] - 1); za = fmaxf(za, (float)fabs(myz[k]) * 1.0000002f); }
-      for (int o = 16; o > 0; o >>= 1) {
-        m |= __shfl_xor_sync(0xffffffffu, m, o);
-        za = fmaxf(za, __shfl_xor_sync(0xffffffffu, za, o));
-      }
-      // equally spaced slots?  D from lane 0 (slots 0,1 are always valid when nz >= 64)
-      const double D = __shfl_sync(0xffffffffu, myz[1] - myz[0], 0);
-      const double tol = 4.0 * 2.220446049250313e-16 * (double)za;
-      bool uni = __shfl_sync(0xffffffffu, (int)(zvalid[0] && zvalid[1]), 0) != 0;
+        for (int k = 0; k < ZL; ++k)
+          if (zvalid[k]) { m |= 1 << (mylay[k] - 1); za = fmaxf(za, (float)fabs(myz[k]) * 1.0000002f); }
+        for (int o = 16; o > 0; o >>= 1) {
+          m |= __shfl_xor_sync(0xffffffffu, m, o);
+          za = fmaxf(za, __shfl_xor_sync(0xffffffffu, za, o));
+        }
+        // equally spaced slots?  D from lane 0 (slots 0,1 are always valid when nz >= 64)
+        const double D = __shfl_sync(0xffffffffu, myz[1] - myz[0], 0);
+        const double tol = 4.0 * 2.220446049250313e-16 * (double)za;
+        bool uni = __shfl_sync(0xffffffffu, (int)(zvalid[0] && zvalid[1]), 0) != 0;
 #pragma unroll
-      for (int k = 0; k + 1 < ZL; ++k)
-        if (zvalid[k] && zvalid[k + 1] && !(fabs((myz[k + 1] - myz[k]) - D) <= tol)) uni = false;
-      uni = __all_sync(0xffffffffu, uni);
-      if (lane == 0) {
-        s_misc[0] = m;
-        s_misc[1] = __float_as_int(za);
-        s_misc[2] = uni ? 1 : 0;
-        *(double *)(s_misc + 6) = D;
+        for (int k = 0; k + 1 < ZL; ++k)
+          if (zvalid[k] && zvalid[k + 1] && !(fabs((myz[k + 1] - myz[k]) - D) <= tol)) uni = false;
+        uni = __all_sync(0xffffffffu, uni);
+        if (lane == 0) {
+          s_misc[0] = m;
+          s_misc[1] = __float_as_int(za);
+          s_misc[2] = uni ? 1 : 0;
+          *(double *)(s_misc + 6) = D;
+        }
       }
     }
     __syncthreads();
     PROF_ADD(1);
-    const int lay_mask = s_misc[0];
+    const int lay_mask = have_cur ? s_misc[0] : 1;
     const double eta_max = fast_eta_max(P, lay_mask, (double)__int_as_float(s_misc[1]));
     const bool zuni = s_misc[2] != 0;
     const double Dz = *(double *)(s_misc + 6);
@@ -1269,15 +1367,55 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       }
       myL[k] = mylay[k] - 1;
     }
-
     const int Lpack = myL[0] | (myL[1] << 2) | (myL[2] << 4) | (myL[3] << 6);
     const bool same_layer = (lay_mask & (lay_mask - 1)) == 0;   // one layer in the whole block
+    // slots whose lanes are not all on the layer of (slot 0, lane 0); exactly one such slot
+    // gets the cheaper "exception" loop
+    const int Lc = __shfl_sync(0xffffffffu, myL[0], 0);
+    int offmask = 0;
+#pragma unroll
+    for (int k = 0; k < ZL; ++k)
+      if (!__all_sync(0xffffffffu, myL[k] == Lc)) offmask |= 1 << k;
+    const int kx = (offmask != 0 && (offmask & (offmask - 1)) == 0) ? __ffs(offmask) - 1 : -1;
+    int Lx = myL[0];
+#pragma unroll
+    for (int k = 1; k < ZL; ++k) if (k == kx) Lx = myL[k];
 
-    // ---- phase A+B per p ---------------------------------------------------------
+    const int njobs_p = have_cur ? np : 0;
+    const int njobs_d = have_prev ? (2 * prev_nzv + 31) / 32 : 0;
     StageEnt4 *stage = s_stage + warp * 32;
     int *okv = s_ok + warp * 32;
-    int stale = 0;
-    for (int pi = warp; pi < np; pi += NW) {
+    for (;;) {
+      int job = 0;
+      if (lane == 0) job = atomicAdd(&s_misc[8], 1);
+      job = __shfl_sync(0xffffffffu, job, 0);
+      if (job >= njobs_p + njobs_d) break;
+      if (job >= njobs_p) {
+        // ---- D-job: de Hoog for 32 (z, value|derivative) pairs of the PREVIOUS item ------
+        const int idx = (job - njobs_p) * 32 + lane;
+        if (idx < 2 * prev_nzv) {
+          const int deriv = idx >= prev_nzv ? 1 : 0;
+          const int zi = idx - deriv * prev_nzv;
+          const double ptee = P.tee_mult * prev_tD;
+#ifdef UNC_SKIP_DEHOOG
+          double v = tot_prev[zi].re;
+#else
+          double v = dehoog_lane(P, tot_prev + zi, ZB, deriv != 0, prev_tD, ptee);
+#endif
+          const long long o = prev_col * (long long)J.nz + prev_z0 + zi;
+          if (deriv) J.ds[o] = v * prev_tD;  // driver.f90:228
+          else {
+            J.s[o] = v;
+            if (J.flags) J.flags[o] = flag_prev[zi];
+          }
+        }
+        __syncwarp();
+        PROF_ADD(6);
+        continue;
+      }
+      // ---- p-job: Hankel quadrature + Wynn for one Laplace parameter, 128 z ----------
+      const int pi = job;
+      int stale = 0;
       const cplx pp = T.p[pi], aux = T.aux[pi], aux2 = T.aux2[pi];
       cplx series[ZL][UNC_MAX_NACC];
       cplx acc[ZL], fin[ZL];
@@ -1313,6 +1451,12 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
             // hot loop: one exp+sincos for slot 0, complex-multiply recurrence for slots 1..3
 #ifndef UNC_SKIP_HOT
             if (same_layer) hot_run_same(stage, j, jend, myz[0], myL[0], acc);
+#ifndef UNC_NO_EXC
+            else if (kx == 3) hot_run_exc<3>(stage, j, jend, myz[0], Lc, Lx, acc);
+            else if (kx == 2) hot_run_exc<2>(stage, j, jend, myz[0], Lc, Lx, acc);
+            else if (kx == 1) hot_run_exc<1>(stage, j, jend, myz[0], Lc, Lx, acc);
+            else if (kx == 0) hot_run_exc<0>(stage, j, jend, myz[0], Lc, Lx, acc);
+#endif
             else hot_run_mixed(stage, j, jend, myz[0], Lpack, acc);
 #endif
             j = jend;
@@ -1376,6 +1520,7 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       for (int k = 0; k < ZL; ++k) { if (seg == 0) fin[k] = acc[k]; else series[k][seg - 1] = acc[k]; }
       const double nan = __longlong_as_double(0x7ff8000000000000LL);
       const cplx lt = T.lt[pi];
+      int live = 0;
 #pragma unroll
       for (int k = 0; k < ZL; ++k) {
         bool any = false;
@@ -1386,41 +1531,33 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
           series[k][j] = a;
           if (fin_a && (a.re != 0.0 || a.im != 0.0)) any = true;  // abs(GLarea) > 0, driver.f90:209
         }
-        cplx infint = mk(0.0, 0.0);
-#ifdef UNC_SKIP_WYNN
-        if (any) infint = series[k][0];
-#else
-        if (any) infint = wynn_any(series[k], nacc);
-#endif
+        if (any) live |= 1 << k;
         else stale |= 1 << k;
+      }
+      cplx infint[ZL];
+#pragma unroll
+      for (int k = 0; k < ZL; ++k) infint[k] = mk(0.0, 0.0);
+#if defined(UNC_SKIP_WYNN)
+#pragma unroll
+      for (int k = 0; k < ZL; ++k) if (live & (1 << k)) infint[k] = series[k][0];
+#else
+#pragma unroll
+      for (int k = 0; k < ZL; ++k) if (live & (1 << k)) infint[k] = wynn_grid(series[k], nacc);
+#endif
+#pragma unroll
+      for (int k = 0; k < ZL; ++k) {
         cplx f = fin[k];
         f = is_finite_fastc(f) ? f * lt : mk(nan, nan);
-        tot[(size_t)pi * ZB + 32 * k + lane] = f + infint;   // totlap, driver.f90:216
+        tot[(size_t)pi * ZB + 32 * k + lane] = f + infint[k];   // totlap, driver.f90:216
       }
+#pragma unroll
+      for (int k = 0; k < ZL; ++k) if (stale & (1 << k)) atomicOr(&flag_cur[32 * k + lane], 1);
       PROF_ADD(4);
     }
-#pragma unroll
-    for (int k = 0; k < ZL; ++k) if (stale & (1 << k)) atomicOr(&s_flag[32 * k + lane], 1);
-    __syncthreads();   // totlap (global, this CTA's slot) and flags complete
     PROF_ADD(5);
-
-    // ---- phase C: de Hoog, one inversion per thread ---------------------------------
-    for (int job = tid; job < 2 * nzv; job += NW * 32) {
-      const int deriv = job >= nzv ? 1 : 0;
-      const int zi = job - deriv * nzv;
-#ifdef UNC_SKIP_DEHOOG
-      double v = tot[zi].re;
-#else
-      double v = dehoog_lane(P, tot + zi, ZB, deriv ? T.p : nullptr, tD, tee);
-#endif
-      const long long o = col * (long long)J.nz + z0 + zi;
-      if (deriv) J.ds[o] = v * tD;  // driver.f90:228
-      else {
-        J.s[o] = v;
-        if (J.flags) J.flags[o] = s_flag[zi];
-      }
-    }
-    PROF_ADD(6);
+    have_prev = have_cur;
+    prev_col = col; prev_z0 = z0; prev_nzv = nzv; prev_tD = tD;
+    buf ^= 1;
   }
 }
 

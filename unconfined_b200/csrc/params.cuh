@@ -11,6 +11,7 @@ namespace unc {
 struct DevParams {
   int model, M, np, N, R, G, nacc, gl_rounds, nts_pad, time_type, n_time_par, moench_M, n_j0z;
   double alpha, log_tol, tee_mult, kappa, alphaD, beta, lD, dD, bD, rDw, CDw, tDb, lD1, dD1;
+  double mn_vartheta, mn_u0;   // model 6 / MNtype 1 (laplace_hankel_solutions.f90:424-431)
   const double *ts_T;          // [N]   tanh(u2)+1           (integration.f90:62)
   const double *ts_wc;         // [N]   Richardson-combined tanh-sinh weights
   const double *gl_x;          // [G]   Gauss-Lobatto interior nodes

@@ -43,6 +43,59 @@ __host__ __device__ __noinline__ cplx wynn_dev(const cplx *series, int nacc) {
   return Y[2];
 }
 
+// Column order as wynn_dev, but a column is processed without the early exit inside it (the
+// first |denom| <= epsilon of the column is remembered and returned after the column; what
+// the later entries of that column hold no longer matters) and in blocks of four rows whose
+// loads are issued together: the table lives in L2-backed local memory and one dependent
+// round trip per entry is what the plain loop costs.
+__host__ __device__ __noinline__ cplx wynn_blk(const cplx *series, int nacc) {
+  cplx X[UNC_MAX_NACC + 4], Y[UNC_MAX_NACC + 4];  // 1-based; X: odd columns (starts as col -1), Y: even
+  int ns = nacc;
+  cplx run = mk(0.0, 0.0);
+  for (int i = 1; i <= nacc; ++i) {
+    if (!is_finite_fastc(series[i - 1])) {
+      ns = i - 1;
+      break;
+    }
+    run = run + series[i - 1];
+    Y[i] = run;
+    X[i] = mk(0.0, 0.0);
+  }
+  if (ns < nacc && ns < 4) return mk(-999999.875, 0.0);  // real(4) literal -999999.9
+  const double eps2 = 2.220446049250313e-16 * 2.220446049250313e-16;
+  constexpr int UB = 4;
+  for (int j = 0; j <= ns - 2; ++j) {
+    cplx *cur = (j & 1) ? X : Y;   // column j
+    cplx *oth = (j & 1) ? Y : X;   // column j-1 -> becomes j+1
+    const int mmax = ns - (j + 1);
+    bool hit = false;
+    cplx ret = mk(0.0, 0.0);
+    cplx b = cur[1];
+    for (int m0 = 1; m0 <= mmax; m0 += UB) {
+      cplx a[UB], o[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int m = min(m0 + u, mmax);      // clamped: stays inside the initialised rows
+        a[u] = cur[m + 1];
+        o[u] = oth[m + 1];
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        if (m0 + u <= mmax) {
+          const double dr = a[u].re - b.re, di = a[u].im - b.im;
+          const double n2 = fma(dr, dr, di * di);
+          const double inv = rcp_fast(n2);
+          oth[m0 + u] = mk(fma(dr, inv, o[u].re), fma(-di, inv, o[u].im));
+          if (!(n2 > eps2) && !hit) { hit = true; ret = a[u]; }   // integration.f90:169-177
+          b = a[u];
+        }
+      }
+    }
+    if (hit) return ret;
+  }
+  return Y[2];
+}
+
 // The same algorithm with the epsilon table held in REGISTERS (north_star): anti-diagonal
 // ("moving lozenge") order needs only one entry per column, D[j] = eps(n-j, j) of the last
 // completed anti-diagonal n, instead of two full columns in local memory (which misses L1
