@@ -30,8 +30,23 @@ __global__ void __launch_bounds__(NW * 32, MINB) hot(const StageEnt4 *g_stage, d
   const double z0 = 0.001 * lane;
   const int l0 = reps < 0 ? 1 : 0, l1 = reps < -1 ? 1 : 0, l2 = reps < -2 ? 1 : 0, l3 = (lane >= 29 && reps > 0) ? 1 : 0;
   (void)l0; (void)l1; (void)l2; (void)l3;
+#if MODE == 2
+  // warp-specialised mix without hand-off: every fourth warp only computes per-(a,p) terms,
+  // the others only run the hot loop (do the two instruction streams disturb each other?)
+  if (((threadIdx.x >> 5) & 3) == 3) {
+    double sink = 0.0;
+    for (int r = 0; r < reps * 6; ++r) {
+      StageEnt4 e;
+      const cplx pp = mk(0.3 + 1e-6 * r, 0.7 + 0.01 * lane);
+      bool ok = ap_terms_fast(P, pp, mk(0, 0), mk(0, 0), 1.0 + 0.37 * lane + 1e-3 * r, 1e-3, 3, 690.0, &e.eta, e.co);
+      sink += ok ? e.co[0].cp.re + e.co[1].cm.im + e.eta.re : 0.0;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = sink;
+    return;
+  }
+#endif
   for (int r = 0; r < reps; ++r) {
-#if MODE >= 1
+#if MODE == 1
     {
       StageEnt4 e;
       const cplx pp = mk(0.3 + 1e-6 * r, 0.7 + 0.01 * lane);

@@ -516,18 +516,19 @@ __device__ __noinline__ double dehoog_lane(const DevParams &P, const cplx *f, in
   return exp(gamma * t) / tee * (A2M / B2M).re;
 }
 
-// Wynn-epsilon for the grid kernel.  Measured alternatives (C5a, ms per step): two
-// local-memory columns (wynn_dev) 127.4; epsilon table in registers, anti-diagonal order
-// (wynn_reg<12>, one serial dependency chain) 146; four series in lockstep over local
-// memory 135.4.  UNC_WYNN_REG selects the register variant for experiments.
+// Wynn-epsilon for the grid kernel.  Measured alternatives (C5a, ms per step, same build
+// otherwise): blocked column order without the in-column early exit (wynn_blk) 123.4; plain
+// column order (wynn_dev) 125.6; epsilon table in registers in anti-diagonal order
+// (wynn_reg<12>: no local memory but one serial dependency chain) ~+15%; four series in
+// lockstep over local memory +6%.  UNC_WYNN_REG / UNC_WYNN_PLAIN select the others.
 __device__ __noinline__ cplx wynn_grid(const cplx *series, int nacc) {
 #ifdef UNC_WYNN_REG
   if (nacc <= 12) return wynn_reg<12>(series, nacc);
 #endif
-#ifdef UNC_WYNN_BLK
-  return wynn_blk(series, nacc);
-#else
+#ifdef UNC_WYNN_PLAIN
   return wynn_dev(series, nacc);
+#else
+  return wynn_blk(series, nacc);
 #endif
 }
 
