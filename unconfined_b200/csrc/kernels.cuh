@@ -549,8 +549,11 @@ __host__ __device__ inline size_t smem_bytes(int np, int nacc, int na, int ZT) {
   return (b + 15) & ~(size_t)15;
 }
 
+#ifndef UNC_POINT_MINB
+#define UNC_POINT_MINB 2   // 128 registers, 16 warps per SM: C5b 481 ms vs 595 ms at 226 registers and 8 warps
+#endif
 template <int ZT>
-__global__ void __launch_bounds__(UNC_THREADS)
+__global__ void __launch_bounds__(UNC_THREADS, UNC_POINT_MINB)
 lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job J) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
