@@ -127,6 +127,13 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- arms
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_sample(p_dict, tD, sv, rD, zD, lay, ncols, nthreads=0):
     """Oracle (CPU port) timed on a bounded sample: `ncols` (t,r) columns x all z."""
     from oracle import oracle
@@ -148,14 +155,14 @@ def run_reference(args, rank, world):
     from oracle import oracle
     d, t, r, z = c5a_grid(0)
     p, tD, sv, rD, zD, lay = derive(d, t, r, z, oracle)
-    cores = oracle.num_threads()
+    cores = host_cores()   # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
     ncols = 12 * cores   # ~10-15 s of wall time per step on the host cores
-    cpu_sample(p, tD, sv, rD[:2], zD, lay, 2)  # warm
+    cpu_sample(p, tD, sv, rD[:2], zD, lay, 2, cores)  # warm
     for _ in range(max(0, args.warmup - 1)):
-        cpu_sample(p, tD, sv, rD, zD, lay, max(2, ncols // 4))
+        cpu_sample(p, tD, sv, rD, zD, lay, max(2, ncols // 4), cores)
     times, pts = [], ncols * len(zD)
     for _ in range(args.steps):
-        _, dt, _ = cpu_sample(p, tD, sv, rD, zD, lay, ncols)
+        _, dt, _ = cpu_sample(p, tD, sv, rD, zD, lay, ncols, cores)
         times.append(dt)
     ms = 1e3 * float(np.mean(times))
     val = pts / (ms * 1e-3)
@@ -282,15 +289,25 @@ def run_ours(args, rank, world, local_rank):
         cpu = None
         if world == 1 and not args.no_cpu:
             from oracle import oracle
-            cores = oracle.num_threads()
+            cores = host_cores()
             ncols = 12 * cores
             po, tDo, svo, rDo, zDo, layo = derive(d, t, r, z, oracle)
-            cpu_sample(po, tDo, svo, rDo[:2], zDo, layo, 2)
-            v, dt, s_cpu = cpu_sample(po, tDo, svo, rDo, zDo, layo, ncols)
+            cpu_sample(po, tDo, svo, rDo[:2], zDo, layo, 2, cores)
+            v, dt, s_cpu = cpu_sample(po, tDo, svo, rDo, zDo, layo, ncols, cores)
             cpu = {"value": v, "unit": "points/s", "cores": cores, "kind": "port",
                    "sample": f"{ncols} (t,r) columns x {nz} z = {ncols * nz} points of the C5a grid, "
                              f"{dt:.1f} s of CPU work (oracle port, OpenMP over columns; no Fortran "
                              "compiler in the image)"}
+        # ncu-derived context for the roofline object (one --set full capture, profiles/): DRAM
+        # traffic per launch and the EXECUTED FP64 rate.  `achieved` counts the algorithmic flops of
+        # SURVEY 8(d) (what the reference's formulas need); the kernel executes ~2.8x fewer (closed
+        # forms, z-recurrence, early stop), so frac can exceed 1 while the pipe itself is ~60% busy.
+        ncu = None
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_grid4_v13_summary.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        traffic = ncu["dram_bytes_per_point"] * npts if ncu else None
         line = {"metric": "drawdown points/sec (r,z,t)", "value": value, "unit": "points/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -306,8 +323,16 @@ def run_ours(args, rank, world, local_rank):
                         "d2h_bytes_per_step": int(16 * npts), "device_equals_host_path": same},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak / 1e12,
-                             "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                             "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                              "flops_per_point": F,
+                             "executed": None if not ncu else {
+                                 "flop_per_point": ncu["executed_fp64_flop_per_point"],
+                                 "frac_of_peak": ncu["executed_fp64_flop_per_point"] * npts / (ms_per_step * 1e-3) / peak,
+                                 "fp64_pipe_pct_ncu": ncu["fp64_pipe_pct_of_peak_active"],
+                                 "source": "profiles/r01_ncu_grid4_v13_summary.json (flop count from ncu, time from this run)"},
+                             "traffic_note": "DRAM bytes per launch scaled from the ncu capture (41 KB/point: "
+                                             "L2-evicted local memory of the de Hoog/Wynn tables; algorithmic "
+                                             "bytes are 16 B/point); 5% of HBM bandwidth, the bound is FP64",
                              "peak_source": "DFMA-chain microbenchmark measured in this run "
                                             "(MEASURED_PEAKS.json has no FP64 entry); nominal 37.2"},
                 "cpu_baseline": cpu}

@@ -32,6 +32,8 @@ module unconfined_b200
      real(c_double)     :: kappa, alphaD, beta
      real(c_double)     :: lD, dD, bD, rDw
      real(c_double)     :: l, d, Ss, rDwobs, sF
+     integer(c_int32_t) :: mn_type, mn_reserved
+     real(c_double)     :: mn_ak, mn_psia, mn_psik, mn_b, mn_Sy
   end type unc_params
 
   interface
@@ -170,6 +172,9 @@ contains
     prm%kappa = f%kappa;  prm%alphaD = f%alphaD;  prm%beta = f%beta
     prm%lD = w%lD;  prm%dD = w%dD;  prm%bD = w%bD;  prm%rDw = w%rDw
     prm%l = w%l;  prm%d = w%d;  prm%Ss = f%Ss;  prm%rDwobs = s%rDwobs;  prm%sF = s%sF
+    ! model 6 / MNtype 1 (laplace_hankel_solutions.f90:404-442)
+    prm%mn_type = s%MNtype;  prm%mn_reserved = 0
+    prm%mn_ak = f%ak;  prm%mn_psia = f%psia;  prm%mn_psik = f%psik;  prm%mn_b = f%b;  prm%mn_Sy = f%Sy
   end subroutine unc_fill_params
 
   function unc_last_error() result(msg)
