@@ -61,10 +61,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) hot(const StageEnt4 *g_stage, d
     for (int j = 0; j < 32; ++j) {
       const StageEnt4 &e = stage[j];
 #ifdef MIXED
-      eval4_recur(e, e.co[l0], e.co[l1], e.co[l2], e.co[l3], z0, acc);
+      eval4_recur<0>(e, e.co[l0], e.co[l1], e.co[l2], e.co[l3], z0, acc);
 #else
       const Coef c0 = e.co[0];
-      eval4_recur(e, c0, c0, c0, c0, z0, acc);
+      eval4_recur<0>(e, c0, c0, c0, c0, z0, acc);
 #endif
     }
   }

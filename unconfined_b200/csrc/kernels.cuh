@@ -409,13 +409,14 @@ __device__ __noinline__ double dehoog_warp(const DevParams &P, const cplx *f, in
 // Complex quotient for the q-d table: a * conj(b)/|b|^2 with the hardware reciprocal + two
 // Newton steps (<= ~2 ulp) while |b| is far from the over/underflow of |b|^2; otherwise the
 // reference's own Smith division, so zero/huge/tiny divisors keep their Inf/NaN flow.
+__device__ __noinline__ cplx cdiv_smith(cplx a, cplx b) { return a / b; }   // rare: kept out of line
 __device__ __forceinline__ cplx cdiv_q(cplx a, cplx b) {
   const double m = fmax(fabs(b.re), fabs(b.im));
   if (m > 1e-140 && m < 1e140) {
     const double inv = rcp_fast(fma(b.re, b.re, b.im * b.im));
     return cmulf(a, mk(b.re * inv, -(b.im * inv)));
   }
-  return a / b;
+  return cdiv_smith(a, b);
 }
 
 // The same inversion done by ONE thread (lane-parallel over inversions): the warp version
@@ -1087,6 +1088,10 @@ __host__ __device__ inline size_t grid4_smem_bytes(int np, int na_seq, int NW) {
   return (b + 15) & ~(size_t)15;
 }
 
+// ZMASK: bit k set = the coefficients of slot k have k0 == 0 exactly (layers below/above the
+// screen of models 1,2,3,5): the four products are then accumulated straight into acc[k]
+// (4 FMA per component) instead of forming f = k0 + ... first and adding it (4 FMA + 1 add).
+template <int ZMASK>
 __device__ __forceinline__ void eval4_recur(const StageEnt4 &e, const Coef &c0, const Coef &c1,
                                             const Coef &c2, const Coef &c3, double z0, cplx *acc) {
   double ep, em, cc, ss, s, cs;
@@ -1098,15 +1103,27 @@ __device__ __forceinline__ void eval4_recur(const StageEnt4 &e, const Coef &c0, 
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const Coef &c = *cf[k];
-    double fr = fma(c.cp.re, Ep.re, c.k0.re);
-    fr = fma(-c.cp.im, Ep.im, fr);
-    fr = fma(c.cm.re, Em.re, fr);
-    fr = fma(-c.cm.im, Em.im, fr);
-    double fi = fma(c.cp.re, Ep.im, c.k0.im);
-    fi = fma(c.cp.im, Ep.re, fi);
-    fi = fma(c.cm.re, Em.im, fi);
-    fi = fma(c.cm.im, Em.re, fi);
-    acc[k] = mk(acc[k].re + fr, acc[k].im + fi);
+    if (ZMASK & (1 << k)) {
+      double fr = fma(c.cp.re, Ep.re, acc[k].re);
+      fr = fma(-c.cp.im, Ep.im, fr);
+      fr = fma(c.cm.re, Em.re, fr);
+      fr = fma(-c.cm.im, Em.im, fr);
+      double fi = fma(c.cp.re, Ep.im, acc[k].im);
+      fi = fma(c.cp.im, Ep.re, fi);
+      fi = fma(c.cm.re, Em.im, fi);
+      fi = fma(c.cm.im, Em.re, fi);
+      acc[k] = mk(fr, fi);
+    } else {
+      double fr = fma(c.cp.re, Ep.re, c.k0.re);
+      fr = fma(-c.cp.im, Ep.im, fr);
+      fr = fma(c.cm.re, Em.re, fr);
+      fr = fma(-c.cm.im, Em.im, fr);
+      double fi = fma(c.cp.re, Ep.im, c.k0.im);
+      fi = fma(c.cp.im, Ep.re, fi);
+      fi = fma(c.cm.re, Em.im, fi);
+      fi = fma(c.cm.im, Em.re, fi);
+      acc[k] = mk(acc[k].re + fr, acc[k].im + fi);
+    }
     if (k < 3) { Ep = cmulf(Ep, e.sp); Em = cmulf(Em, e.sm); }
   }
 }
@@ -1120,6 +1137,7 @@ __device__ __forceinline__ void eval4_recur(const StageEnt4 &e, const Coef &c0, 
 #define UNC_HOT_UNROLL 1
 #endif
 constexpr int kHotUnroll = UNC_HOT_UNROLL;
+template <bool K0Z>
 __device__ __noinline__ void hot_run_same(const StageEnt4 *stage, int j, int jend, double z0, int L,
                                           cplx *acc_io) {
   cplx acc[4];
@@ -1129,7 +1147,7 @@ __device__ __noinline__ void hot_run_same(const StageEnt4 *stage, int j, int jen
   for (; j < jend; ++j) {
     const StageEnt4 &e = stage[j];
     const Coef c = e.co[L];
-    eval4_recur(e, c, c, c, c, z0, acc);
+    eval4_recur<K0Z ? 15 : 0>(e, c, c, c, c, z0, acc);
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) acc_io[k] = acc[k];
@@ -1144,7 +1162,7 @@ __device__ __noinline__ void hot_run_mixed(const StageEnt4 *stage, int j, int je
 #pragma unroll kHotUnroll
   for (; j < jend; ++j) {
     const StageEnt4 &e = stage[j];
-    eval4_recur(e, e.co[l0], e.co[l1], e.co[l2], e.co[l3], z0, acc);
+    eval4_recur<0>(e, e.co[l0], e.co[l1], e.co[l2], e.co[l3], z0, acc);
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) acc_io[k] = acc[k];
@@ -1154,7 +1172,7 @@ __device__ __noinline__ void hot_run_mixed(const StageEnt4 *stage, int j, int je
 // case of a z-block that straddles a layer boundary (z ascending, so the boundary falls in
 // one slot).  Three broadcast loads for the common coefficients plus three per-lane ones,
 // instead of twelve per-lane loads and four coefficient sets in registers.
-template <int KX>
+template <int KX, bool K0Z>
 __device__ __noinline__ void hot_run_exc(const StageEnt4 *stage, int j, int jend, double z0, int L,
                                          int Lx, cplx *acc_io) {
   cplx acc[4];
@@ -1164,7 +1182,7 @@ __device__ __noinline__ void hot_run_exc(const StageEnt4 *stage, int j, int jend
     const StageEnt4 &e = stage[j];
     const Coef c = e.co[L];
     const Coef cx = e.co[Lx];
-    eval4_recur(e, KX == 0 ? cx : c, KX == 1 ? cx : c, KX == 2 ? cx : c, KX == 3 ? cx : c, z0, acc);
+    eval4_recur<K0Z ? (15 & ~(1 << KX)) : 0>(e, KX == 0 ? cx : c, KX == 1 ? cx : c, KX == 2 ? cx : c, KX == 3 ? cx : c, z0, acc);
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) acc_io[k] = acc[k];
@@ -1384,6 +1402,8 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
     int Lx = myL[0];
 #pragma unroll
     for (int k = 1; k < ZL; ++k) if (k == kx) Lx = myL[k];
+    // k0 of the common layer is exactly zero below/above the screen of the Hantush-type models
+    const bool k0z = (P.model == 1 || P.model == 2 || P.model == 3 || P.model == 5) && Lc != 1;
 
     const int njobs_p = have_cur ? np : 0;
     const int njobs_d = have_prev ? (2 * prev_nzv + 31) / 32 : 0;
@@ -1435,6 +1455,8 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       const bool lt_ok = is_finite_fastc(lt_chk) && (lt_chk.re != 0.0 || lt_chk.im != 0.0);
       int dead = 0, anyf = 0;
       bool done = false;
+      // (measured: starting half of the warps with a half chunk to de-synchronise the
+      // ap_terms / hot-loop phases of the warps sharing a scheduler is 2% SLOWER)
       for (int base = 0; base < NA && !done; base += 32) {
         int ok = 1;
         {
@@ -1454,14 +1476,20 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
           if (all_ok && zuni) {
             // hot loop: one exp+sincos for slot 0, complex-multiply recurrence for slots 1..3
 #ifndef UNC_SKIP_HOT
-            if (same_layer) hot_run_same(stage, j, jend, myz[0], myL[0], acc);
-#ifndef UNC_NO_EXC
-            else if (kx == 3) hot_run_exc<3>(stage, j, jend, myz[0], Lc, Lx, acc);
-            else if (kx == 2) hot_run_exc<2>(stage, j, jend, myz[0], Lc, Lx, acc);
-            else if (kx == 1) hot_run_exc<1>(stage, j, jend, myz[0], Lc, Lx, acc);
-            else if (kx == 0) hot_run_exc<0>(stage, j, jend, myz[0], Lc, Lx, acc);
-#endif
-            else hot_run_mixed(stage, j, jend, myz[0], Lpack, acc);
+            if (same_layer) {
+              if (k0z) hot_run_same<true>(stage, j, jend, myz[0], myL[0], acc);
+              else hot_run_same<false>(stage, j, jend, myz[0], myL[0], acc);
+            } else if (kx >= 0 && k0z) {
+              if (kx == 3) hot_run_exc<3, true>(stage, j, jend, myz[0], Lc, Lx, acc);
+              else if (kx == 2) hot_run_exc<2, true>(stage, j, jend, myz[0], Lc, Lx, acc);
+              else if (kx == 1) hot_run_exc<1, true>(stage, j, jend, myz[0], Lc, Lx, acc);
+              else hot_run_exc<0, true>(stage, j, jend, myz[0], Lc, Lx, acc);
+            } else if (kx >= 0) {
+              if (kx == 3) hot_run_exc<3, false>(stage, j, jend, myz[0], Lc, Lx, acc);
+              else if (kx == 2) hot_run_exc<2, false>(stage, j, jend, myz[0], Lc, Lx, acc);
+              else if (kx == 1) hot_run_exc<1, false>(stage, j, jend, myz[0], Lc, Lx, acc);
+              else hot_run_exc<0, false>(stage, j, jend, myz[0], Lc, Lx, acc);
+            } else hot_run_mixed(stage, j, jend, myz[0], Lpack, acc);
 #endif
             j = jend;
           } else {
