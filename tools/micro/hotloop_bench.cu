@@ -18,6 +18,12 @@ constexpr int kUnroll = UNROLL;
 #ifndef MODE
 #define MODE 0
 #endif
+#ifndef BEXC
+#define BEXC -1
+#endif
+#ifndef BK0Z
+#define BK0Z false
+#endif
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, MINB) hot(const StageEnt4 *g_stage, double *out, int reps, DevParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -42,6 +48,28 @@ __global__ void __launch_bounds__(NW * 32, MINB) hot(const StageEnt4 *g_stage, d
       sink += ok ? e.co[0].cp.re + e.co[1].cm.im + e.eta.re : 0.0;
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = sink;
+    return;
+  }
+#endif
+#if MODE == 3
+  // eight z-slots per lane, two p per warp (half-warps read different stage entries)
+  {
+    StageEnt8 *st8 = (StageEnt8 *)smem + (threadIdx.x >> 5) * 32;
+    {
+      StageEnt8 t;
+      const StageEnt4 &g = g_stage[lane];
+      t.eta = g.eta; t.co[0] = g.co[0]; t.co[1] = g.co[1]; t.co[2] = g.co[2];
+      t.sp = g.sp; t.sm = g.sm; t.spx = g.sp; t.smx = g.sm;
+      st8[lane] = t;
+    }
+    __syncwarp();
+    cplx a8[8];
+    for (int k = 0; k < 8; ++k) a8[k] = mk(0, 0);
+    const int half = lane >> 4;
+    const int Lx = (lane & 15) >= 13 ? 1 : 0;
+    for (int r = 0; r < reps; ++r) hot8_run<BEXC, BK0Z>(st8 + half * 16, 0, 16, z0, 0, Lx, a8);
+    double t = 0; for (int k = 0; k < 8; ++k) t += a8[k].re + a8[k].im;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = t;
     return;
   }
 #endif
@@ -85,7 +113,7 @@ int main(int argc, char **argv) {
   int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int grid = sms * MINB;
   cudaMalloc(&o, sizeof(double) * grid * NW * 32);
-  size_t smem = NW * 32 * sizeof(StageEnt4) + PADSMEM;
+  size_t smem = NW * 32 * sizeof(StageEnt8) + PADSMEM;
   cudaFuncSetAttribute(hot<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   int occ; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hot<NW>, NW * 32, smem);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);

@@ -265,7 +265,7 @@ struct DevCtx {
   DevBuf tables, in, out, scratch, counter;
   int sm_count = 0;
   std::vector<double> blob_cached;
-  bool smem_set[16] = {false};
+  bool smem_set[32] = {false};
 };
 DevCtx g_ctx[16];
 
@@ -375,6 +375,37 @@ int launch_grid4_nw(int dev, const unc::DevParams &P, const unc::Job &J, cudaStr
   return UNC_OK;
 }
 
+// second generation: eight z-slots per lane, two Laplace parameters per warp (lh_grid8_kernel)
+template <int NW>
+int launch_grid8_nw(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
+  const int NA = P.N + P.nacc * P.G;
+  const size_t smem = unc::grid8_smem_bytes(P.np, (NA + 31) & ~31, NW);
+  if (smem > 227 * 1024) return fail(UNC_ERR_UNSUPPORTED, "shared memory need %zu B exceeds 227 KB", smem);
+  DevCtx &c = g_ctx[dev];
+  if (!c.smem_set[20]) {
+    CK(cudaFuncSetAttribute(unc::lh_grid8_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    c.smem_set[20] = true;
+  }
+  const long long nitems = J.ncol * ((J.nz + 127) / 128);
+  if (nitems <= 0) return UNC_OK;
+  if (nitems > 4000000000LL) return fail(UNC_ERR_UNSUPPORTED, "too many work items (%lld)", nitems);
+  int occ = 2;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, unc::lh_grid8_kernel<NW>, NW * 32, smem));
+  if (occ < 1) occ = 1;
+  const int grid = (int)std::min<long long>(nitems, (long long)c.sm_count * occ);
+  int rc = c.scratch.ensure((size_t)grid * 2 * P.np * 128 * sizeof(unc::cplx));   // two totlap slots per CTA
+  if (rc) return rc;
+  const bool fresh_counter = c.counter.ptr == nullptr;
+  rc = c.counter.ensure(256);
+  if (rc) return rc;
+  if (fresh_counter) CK(cudaMemsetAsync(c.counter.ptr, 0, 256, st));   // the kernel re-arms it itself
+  unc::lh_grid8_kernel<NW><<<grid, NW * 32, smem, st>>>(P, J, (unc::cplx *)c.scratch.ptr,
+                                                         (unsigned int *)c.counter.ptr);
+  g_launches++;
+  CK(cudaGetLastError());
+  return UNC_OK;
+}
+
 int launch_grid4(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
 #ifdef UNC_GRID4_NW
   return launch_grid4_nw<UNC_GRID4_NW>(dev, P, J, st);   // experiments (tools/run_variants.sh)
@@ -386,6 +417,8 @@ int launch_grid4(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream
 int launch_grid(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
   const char *force = getenv("UNC_FORCE_KERNEL");
   const bool no4 = force && !strcmp(force, "grid2");
+  const bool only4 = force && !strcmp(force, "grid4");
+  if (J.nz >= 96 && !no4 && !only4) return launch_grid8_nw<8>(dev, P, J, st);
   if (J.nz >= 96 && !no4) return launch_grid4(dev, P, J, st);
   // two z per lane (64 z per CTA) halves the per-(a,p) work per point; keep one z per lane
   // for short columns and when the larger totlap tile would not fit twice per SM
@@ -399,7 +432,7 @@ int launch(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st)
   const char *force = getenv("UNC_FORCE_KERNEL");
   bool grid = J.nz >= 12;
   if (force && !strcmp(force, "point")) grid = false;
-  if (force && (!strcmp(force, "grid") || !strcmp(force, "grid2"))) grid = true;
+  if (force && (!strcmp(force, "grid") || !strcmp(force, "grid2") || !strcmp(force, "grid4"))) grid = true;
   if (grid) return launch_grid(dev, P, J, st);
   if (J.nz >= 4) return launch_zt<4>(dev, P, J, st);
   if (J.nz >= 2) return launch_zt<2>(dev, P, J, st);

@@ -1128,6 +1128,74 @@ __device__ __forceinline__ void eval4_recur(const StageEnt4 &e, const Coef &c0, 
   }
 }
 
+// ---------------------------------------------------------------------------
+// Eight z-slots per lane, two Laplace parameters per warp (lh_grid8_kernel below).
+struct StageEnt8 {
+  cplx eta;
+  Coef co[3];
+  cplx sp, sm;    // exp(+-eta*D), D = z spacing between a lane's slots (16 grid steps)
+  cplx spx, smx;  // exp(+-eta*D*kx): straight to the one slot with lane-dependent layers
+};
+
+// One abscissa for the eight slots of a lane.  The slot values of the common-layer slots are
+// advanced ALREADY SCALED by the coefficients, P_k = cp e^{eta z_k}, M_k = cm e^{-eta z_k}
+// (P_{k+1} = P_k e^{eta D}, M_{k+1} = M_k e^{-eta D}: two first-order recurrences, each
+// stable in its own direction), so a slot costs 2 complex multiplies + 2 complex adds
+// instead of 2 multiplies + 8 FMA.  Slot KX (if >= 0) has lane-dependent layers: its
+// exponentials come from slot 0 in one step (spx, smx) and take the per-lane cx.
+// K0Z: k0 of the common layer is exactly zero.
+template <int KX, bool K0Z>
+__device__ __forceinline__ void eval8_scaled(const StageEnt8 &e, const Coef &c, const Coef &cx, double z0,
+                                             cplx *acc) {
+  double ep, em, cc, ss, s, cs;
+  int kk;
+  exp_pm_core(e.eta.re * z0, &ep, &em, &cc, &ss, &kk);
+  sincos_q(e.eta.im * z0, &s, &cs);
+  const cplx Ep = mk(ep * cs, ep * s), Em = mk(em * cs, -(em * s));
+  if (KX >= 0) {
+    const cplx Ex = (KX == 0) ? Ep : cmulf(Ep, e.spx), Mx = (KX == 0) ? Em : cmulf(Em, e.smx);
+    double fr = fma(cx.cp.re, Ex.re, cx.k0.re);
+    fr = fma(-cx.cp.im, Ex.im, fr);
+    fr = fma(cx.cm.re, Mx.re, fr);
+    fr = fma(-cx.cm.im, Mx.im, fr);
+    double fi = fma(cx.cp.re, Ex.im, cx.k0.im);
+    fi = fma(cx.cp.im, Ex.re, fi);
+    fi = fma(cx.cm.re, Mx.im, fi);
+    fi = fma(cx.cm.im, Mx.re, fi);
+    acc[KX < 0 ? 0 : KX] = mk(acc[KX < 0 ? 0 : KX].re + fr, acc[KX < 0 ? 0 : KX].im + fi);
+  }
+  cplx Pk = cmulf(c.cp, Ep), Mk = cmulf(c.cm, Em);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k != KX) {
+      double fr = Pk.re + Mk.re, fi = Pk.im + Mk.im;
+      if (!K0Z) { fr += c.k0.re; fi += c.k0.im; }
+      acc[k] = mk(acc[k].re + fr, acc[k].im + fi);
+    }
+    if (k < 7 && !(KX == 7 && k == 6)) { Pk = cmulf(Pk, e.sp); Mk = cmulf(Mk, e.sm); }
+  }
+}
+
+template <int KX, bool K0Z>
+__device__ __noinline__ void hot8_run(const StageEnt8 *stage, int j, int jend, double z0, int L, int Lx,
+                                      cplx *acc_io) {
+  cplx acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = acc_io[k];
+  for (; j < jend; ++j) {
+    const StageEnt8 &e = stage[j];
+    const Coef c = e.co[L];
+    if (KX >= 0) {
+      const Coef cx = e.co[Lx];
+      eval8_scaled<KX, K0Z>(e, c, cx, z0, acc);
+    } else {
+      eval8_scaled<KX, K0Z>(e, c, c, z0, acc);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc_io[k] = acc[k];
+}
+
 // The hot loop as separate functions: the persistent kernel around it keeps ~100 registers
 // of long-lived state, and inlined there the loop was compiled with address
 // rematerialisation (S2R/R2UR) and extra loads; as a call it gets its own register
@@ -1207,6 +1275,39 @@ __device__ __noinline__ int ap_terms_stage(const DevParams &P, cplx p, cplx aux,
   }
   *out = e;
   return ok ? 1 : 0;
+}
+
+// The same for the eight-slot kernel: also exp(+-eta*Dz*kx) for the exception slot kx (>= 1).
+__device__ __noinline__ int ap_terms_stage8(const DevParams &P, cplx p, cplx aux, cplx aux2, double a2,
+                                            double w, int lay_mask, double eta_max, bool zuni,
+                                            double Dz, int kx, StageEnt8 *out) {
+  StageEnt8 e;
+  const bool ok = ap_terms_fast(P, p, aux, aux2, a2, w, lay_mask, eta_max, &e.eta, e.co);
+  e.sp = e.sm = e.spx = e.smx = mk(1.0, 0.0);
+  if (zuni && ok) {
+    const cbundle S = cexp_bundle(e.eta.re * Dz, e.eta.im * Dz);
+    e.sp = S.ep;
+    e.sm = S.em;
+    if (kx >= 1) {
+      const double Dx = Dz * (double)kx;
+      const cbundle X = cexp_bundle(e.eta.re * Dx, e.eta.im * Dx);
+      e.spx = X.ep;
+      e.smx = X.em;
+    }
+  }
+  *out = e;
+  return ok ? 1 : 0;
+}
+
+__host__ __device__ inline size_t grid8_smem_bytes(int np, int na_seq, int NW) {
+  size_t b = 0;
+  b += (size_t)4 * np * sizeof(cplx);
+  b += (size_t)2 * na_seq * sizeof(double);
+  size_t stage = (size_t)NW * 32 * sizeof(StageEnt8) + (size_t)NW * 32 * sizeof(int);
+  size_t scratch = (size_t)NW * 3 * np * sizeof(cplx);
+  b += stage > scratch ? stage : scratch;
+  b += 2 * 128 * sizeof(int) + 64;
+  return (b + 15) & ~(size_t)15;
 }
 
 #ifndef UNC_GRID4_MINB
@@ -1592,6 +1693,412 @@ lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
     buf ^= 1;
   }
 }
+
+// ---------------------------------------------------------------------------
+// Grid kernel, second generation: the job-pool structure of lh_grid4_kernel with EIGHT z-slots
+// per lane and TWO Laplace parameters per warp (lanes 0-15 <-> p = 2*job, lanes 16-31 <->
+// p = 2*job+1; z = z0 + hl + 16 k).  The per-abscissa exponential of slot 0 (48 of the
+// FP64 instructions) is shared by eight z instead of four, the slots advance the products
+// cp*e^{eta z}, cm*e^{-eta z} themselves (eval8_scaled), and a staged abscissa (shared-memory
+// reads) serves twice as many (p,z) pairs.  Requires equally spaced z within an item, which
+// is checked per item as before (any other z-list takes the exact per-slot evaluation).
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, UNC_GRID4_MINB)
+lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job J,
+                cplx *__restrict__ g_tot, unsigned int *__restrict__ g_counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int ZL = 8, ZB = 128, GL = 16;   // 8 slots per lane, 16 lanes per Laplace parameter
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = lane >> 4, hl = lane & 15;   // which of the warp's two p; z lane
+  const int np = P.np, nacc = P.nacc, G = P.G, N = P.N;
+  const int NA = N + nacc * G;
+  const int na_seq = (NA + 31) & ~31;
+  const int nzb = (J.nz + ZB - 1) / ZB;
+  const long long nitems = J.ncol * (long long)nzb;
+
+  unsigned char *sp = smem_raw;
+  PTab T;
+  T.p = (cplx *)sp; sp += np * sizeof(cplx);
+  T.lt = (cplx *)sp; sp += np * sizeof(cplx);
+  T.aux = (cplx *)sp; sp += np * sizeof(cplx);
+  T.aux2 = (cplx *)sp; sp += np * sizeof(cplx);
+  double *s_a2 = (double *)sp; sp += na_seq * sizeof(double);
+  double *s_wj = (double *)sp; sp += na_seq * sizeof(double);
+  StageEnt8 *s_stage = (StageEnt8 *)sp;
+  int *s_ok = (int *)(sp + (size_t)NW * 32 * sizeof(StageEnt8));
+  cplx *s_scr = (cplx *)sp;
+  {
+    size_t stage = (size_t)NW * 32 * sizeof(StageEnt8) + (size_t)NW * 32 * sizeof(int);
+    size_t scratch = (size_t)NW * 3 * np * sizeof(cplx);
+    sp += stage > scratch ? stage : scratch;
+  }
+  int *s_flag = (int *)sp; sp += 2 * 128 * sizeof(int);   // stale flags per z, [buffer][z]
+  int *s_misc = (int *)sp;  // [0] layer mask, [1] max|z| bits, [2] uniform-z flag, [3] item, [6..7] D, [8] job counter
+  cplx *tot_base = g_tot + (size_t)blockIdx.x * 2 * np * ZB;  // this CTA's two totlap slots [p][z]
+
+  // Software pipeline over work items: round i runs the np quadrature jobs ("p-jobs") of
+  // item i AND the de Hoog jobs ("D-jobs", 32 inversions each, one per lane) of item i-1 out
+  // of one job pool that the warps drain through a shared-memory counter.  The small D-jobs
+  // come last, so the warps that run out of p-jobs invert the previous item's totlap while
+  // the others finish: no separate de Hoog phase with every warp stalled on its q-d table,
+  // and the end-of-round barrier waits for a D-job at most, not for a p-job.
+  int buf = 0;
+  bool have_prev = false, dry = false;
+  long long prev_col = 0;
+  int prev_z0 = 0, prev_nzv = 0;
+  double prev_tD = 0.0;
+  PROF_T0();
+  for (;;) {
+    __syncthreads();   // every job of the previous round is complete
+    PROF_ADD(0);
+    if (tid == 0) {
+      if (!dry) s_misc[3] = (int)atomicAdd(g_counter, 1u);
+      s_misc[8] = 0;
+    }
+    __syncthreads();
+    const long long item = (unsigned int)s_misc[3];
+    const bool have_cur = item < nitems;
+    if (!have_cur) dry = true;
+    if (!have_cur && !have_prev) {
+      // the last CTA to finish re-arms both counters, so every launch (and every profiler
+      // replay of a launch) starts from zero without a host-side memset
+      if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(g_counter + 1, 1u) == gridDim.x - 1) {
+          g_counter[0] = 0u;
+          g_counter[1] = 0u;
+          __threadfence();
+        }
+      }
+      break;
+    }
+    cplx *tot = tot_base + (size_t)buf * np * ZB;
+    const cplx *tot_prev = tot_base + (size_t)(buf ^ 1) * np * ZB;
+    int *flag_cur = s_flag + buf * 128;
+    const int *flag_prev = s_flag + (buf ^ 1) * 128;
+
+    const long long col = have_cur ? item / nzb : 0;
+    const int z0 = have_cur ? (int)(item % nzb) * ZB : 0;
+    const int nzv = have_cur ? min(ZB, J.nz - z0) : 0;
+    const double tD = J.tD[col / J.tdiv];
+    const int sv = J.sv[col / J.tdiv];
+    const double rD = J.rD[col % J.rmod];
+    const double tee = P.tee_mult * tD;
+    const double arg = P.j0z[sv - 1] / rD;                      // driver.f90:120
+    const double tscale = J.ts_scale ? J.ts_scale[col] : arg;  // driver.f90:121-126
+    const long long zbase = (J.zstride ? col * (long long)J.nz : 0) + z0;
+    double myz[ZL];
+    int mylay[ZL];
+    bool zvalid[ZL];
+#pragma unroll
+    for (int k = 0; k < ZL; ++k) {
+      const int zi = hl + GL * k;
+      zvalid[k] = zi < nzv;
+      myz[k] = zvalid[k] ? J.zD[zbase + zi] : 0.0;
+      mylay[k] = zvalid[k] ? J.zLay[zbase + zi] : 0;
+    }
+
+    // ---- prologue (tables of the current item) -----------------------------------
+    if (have_cur) {
+      if (tid < ZB) flag_cur[tid] = 0;
+      for (int i = tid; i < np; i += NW * 32) {
+        const double PI = 3.141592653589793;
+        double sigma = P.alpha - P.log_tol / (2.0 * tee);   // invlap.f90:166-170
+        cplx p = mk(sigma, PI * (double)i / tee);
+        T.p[i] = p;
+        T.lt[i] = laptime_dev(P, p);
+        cplx aux = mk(0.0, 0.0), aux2 = mk(0.0, 0.0);
+        if (P.model == 3) {
+          for (int m = 0; m < P.moench_M; ++m) aux = aux + 1.0 / (1.0 + p * (1.0 / P.moench_gamma[m]));
+        } else if (P.model == 2) {
+          cplx xi = P.rDw * csqrt_g(p);
+          cplx K[2];
+          cbesk01_dev(xi, K);
+          aux = 2.0 / (p * P.CDw * K[0] + xi * K[1]);
+          aux2 = p * P.tDb + 1.0;
+        }
+        T.aux[i] = aux;
+        T.aux2[i] = aux2;
+      }
+      for (int idx = tid; idx < na_seq; idx += NW * 32) {
+        double a = 0.0, w = 0.0;
+        if (idx < N) {
+          a = (P.ts_T[idx] * tscale) / 2.0;  // integration.f90:62
+          w = P.ts_wc[idx] * (arg / 2.0);    // driver.f90:135,154 + Richardson (linear in tmp)
+        } else if (idx < NA) {
+          const int node = idx - N;
+          const int j = node / G, m = node - j * G;
+          const double lob = P.j0z[sv + j - 1] / rD;  // driver.f90:188-193
+          const double hib = P.j0z[sv + j] / rD;
+          const double width = hib - lob;
+          a = fma(width, P.gl_x[m], hib + lob) / 2.0;
+          w = P.gl_w[m] * (width / 2.0);
+        }
+        s_a2[idx] = a * a;
+        s_wj[idx] = (w != 0.0) ? w * (a * j0_dev(a * rD)) : 0.0;  // laplace_hankel_solutions.f90:118
+      }
+      if (warp == 0) {
+        int m = 0;
+        float za = 0.f;
+#pragma unroll
+        for (int k = 0; k < ZL; ++k)
+          if (zvalid[k]) { m |= 1 << (mylay[k] - 1); za = fmaxf(za, (float)fabs(myz[k]) * 1.0000002f); }
+        for (int o = 16; o > 0; o >>= 1) {
+          m |= __shfl_xor_sync(0xffffffffu, m, o);
+          za = fmaxf(za, __shfl_xor_sync(0xffffffffu, za, o));
+        }
+        // equally spaced slots?  D from lane 0 (slots 0,1 are always valid when nz >= 32)
+        const double D = __shfl_sync(0xffffffffu, myz[1] - myz[0], 0);
+        const double tol = 4.0 * 2.220446049250313e-16 * (double)za;
+        bool uni = __shfl_sync(0xffffffffu, (int)(zvalid[0] && zvalid[1]), 0) != 0;
+#pragma unroll
+        for (int k = 0; k + 1 < ZL; ++k)
+          if (zvalid[k] && zvalid[k + 1] && !(fabs((myz[k + 1] - myz[k]) - D) <= tol)) uni = false;
+        uni = __all_sync(0xffffffffu, uni);
+        if (lane == 0) {
+          s_misc[0] = m;
+          s_misc[1] = __float_as_int(za);
+          s_misc[2] = uni ? 1 : 0;
+          *(double *)(s_misc + 6) = D;
+        }
+      }
+    }
+    __syncthreads();
+    PROF_ADD(1);
+    const int lay_mask = have_cur ? s_misc[0] : 1;
+    const double eta_max = fast_eta_max(P, lay_mask, (double)__int_as_float(s_misc[1]));
+    const bool zuni = s_misc[2] != 0;
+    const double Dz = *(double *)(s_misc + 6);
+    const int L0 = __ffs(lay_mask) - 1;
+    int myL[ZL];
+#pragma unroll
+    for (int k = 0; k < ZL; ++k) {
+      if (!zvalid[k]) {                 // padding slots mimic a present layer / the uniform grid
+        mylay[k] = L0 + 1;
+        myz[k] = zuni ? myz[0] + k * Dz : 0.5;
+        if (!zvalid[0]) myz[k] = 0.5;
+      }
+      myL[k] = mylay[k] - 1;
+    }
+    // slots whose lanes are not all on the layer of (slot 0, lane 0); exactly one such slot
+    // gets the cheaper "exception" loop
+    const int Lc = __shfl_sync(0xffffffffu, myL[0], 0);
+    int offmask = 0;
+#pragma unroll
+    for (int k = 0; k < ZL; ++k)
+      if (!__all_sync(0xffffffffu, myL[k] == Lc)) offmask |= 1 << k;
+    const int kx = (offmask != 0 && (offmask & (offmask - 1)) == 0) ? __ffs(offmask) - 1 : -1;
+    const bool hot_ok = (offmask & (offmask - 1)) == 0;   // at most one slot off the common layer
+    int Lx = myL[0];
+#pragma unroll
+    for (int k = 1; k < ZL; ++k) if (k == kx) Lx = myL[k];
+    // k0 of the common layer is exactly zero below/above the screen of the Hantush-type models
+    const bool k0z = (P.model == 1 || P.model == 2 || P.model == 3 || P.model == 5) && Lc != 1;
+
+    const int njobs_p = have_cur ? (np + 1) / 2 : 0;   // two Laplace parameters per p-job
+    const int njobs_d = have_prev ? (2 * prev_nzv + 31) / 32 : 0;
+    StageEnt8 *stage = s_stage + warp * 32 + half * GL;   // this half-warp's 16 staged abscissae
+    int *okv = s_ok + warp * 32 + half * GL;
+    for (;;) {
+      int job = 0;
+      if (lane == 0) job = atomicAdd(&s_misc[8], 1);
+      job = __shfl_sync(0xffffffffu, job, 0);
+      if (job >= njobs_p + njobs_d) break;
+      if (job >= njobs_p) {
+        // ---- D-job: de Hoog for 32 (z, value|derivative) pairs of the PREVIOUS item ------
+        const int idx = (job - njobs_p) * 32 + lane;
+        if (idx < 2 * prev_nzv) {
+          const int deriv = idx >= prev_nzv ? 1 : 0;
+          const int zi = idx - deriv * prev_nzv;
+          const double ptee = P.tee_mult * prev_tD;
+#ifdef UNC_SKIP_DEHOOG
+          double v = tot_prev[zi].re;
+#else
+          double v = dehoog_lane(P, tot_prev + zi, ZB, deriv != 0, prev_tD, ptee);
+#endif
+          const long long o = prev_col * (long long)J.nz + prev_z0 + zi;
+          if (deriv) J.ds[o] = v * prev_tD;  // driver.f90:228
+          else {
+            J.s[o] = v;
+            if (J.flags) J.flags[o] = flag_prev[zi];
+          }
+        }
+        __syncwarp();
+        PROF_ADD(6);
+        continue;
+      }
+      // ---- p-job: Hankel quadrature + Wynn for two Laplace parameters (one per half-warp),
+      //      128 z each.  np odd: the upper half of the last job repeats p = np-1 and stores nothing.
+      const bool pvalid = 2 * job + half < np;
+      const int pi = min(2 * job + half, np - 1);
+      int stale = 0;
+      const cplx pp = T.p[pi], aux = T.aux[pi], aux2 = T.aux2[pi];
+      // areas[k][0] = tanh-sinh part (finint), areas[k][1..nacc] = Gauss-Lobatto interval areas:
+      // one thread-local array instead of a second register set for the finite part
+      cplx areas[ZL][UNC_MAX_NACC + 1];
+      cplx acc[ZL];
+#pragma unroll
+      for (int k = 0; k < ZL; ++k) { acc[k] = mk(0.0, 0.0); areas[k][0] = mk(0.0, 0.0); }
+      int seg = 0;
+      int next_b = N;
+      // Wynn only uses the areas before the first non-finite one (integration.f90:140-160) and
+      // driver.f90:209 only asks whether SOME area is finite and non-zero.  Once that is settled
+      // for every z of the warp (dead: a non-finite area seen; anyf: a finite non-zero one seen)
+      // the remaining, ever more expensive, overflowing abscissae cannot change the result.
+      const cplx lt_chk = T.lt[pi];
+      const bool lt_ok = is_finite_fastc(lt_chk) && (lt_chk.re != 0.0 || lt_chk.im != 0.0);
+      int dead = 0, anyf = 0;
+      bool done = false;
+      // (measured: starting half of the warps with a half chunk to de-synchronise the
+      // ap_terms / hot-loop phases of the warps sharing a scheduler is 2% SLOWER)
+      for (int base = 0; base < NA && !done; base += GL) {
+        int ok = 1;
+        {
+          const int idx = base + hl;
+          if (idx < NA)
+            ok = ap_terms_stage8(P, pp, aux, aux2, s_a2[idx], s_wj[idx], lay_mask, eta_max, zuni, Dz, kx,
+                                 &stage[hl]);
+          okv[hl] = ok;
+        }
+        const bool all_ok = __all_sync(0xffffffffu, ok);
+        __syncwarp();
+        PROF_ADD(2);
+        const int cnt = min(GL, NA - base);
+        int j = 0;
+        while (j < cnt) {
+          const int jend = min(cnt, next_b - base);
+          if (all_ok && zuni && hot_ok) {
+            // hot loop: one exp+sincos for slot 0, complex-multiply recurrence for slots 1..3
+#ifndef UNC_SKIP_HOT
+            if (kx < 0) {
+              if (k0z) hot8_run<-1, true>(stage, j, jend, myz[0], Lc, Lc, acc);
+              else hot8_run<-1, false>(stage, j, jend, myz[0], Lc, Lc, acc);
+            } else if (k0z) {
+              switch (kx) {
+                case 0: hot8_run<0, true>(stage, j, jend, myz[0], Lc, Lx, acc); break;
+                case 1: hot8_run<1, true>(stage, j, jend, myz[0], Lc, Lx, acc); break;
+                case 2: hot8_run<2, true>(stage, j, jend, myz[0], Lc, Lx, acc); break;
+                case 3: hot8_run<3, true>(stage, j, jend, myz[0], Lc, Lx, acc); break;
+                case 4: hot8_run<4, true>(stage, j, jend, myz[0], Lc, Lx, acc); break;
+                case 5: hot8_run<5, true>(stage, j, jend, myz[0], Lc, Lx, acc); break;
+                case 6: hot8_run<6, true>(stage, j, jend, myz[0], Lc, Lx, acc); break;
+                default: hot8_run<7, true>(stage, j, jend, myz[0], Lc, Lx, acc); break;
+              }
+            } else {
+              switch (kx) {
+                case 0: hot8_run<0, false>(stage, j, jend, myz[0], Lc, Lx, acc); break;
+                case 1: hot8_run<1, false>(stage, j, jend, myz[0], Lc, Lx, acc); break;
+                case 2: hot8_run<2, false>(stage, j, jend, myz[0], Lc, Lx, acc); break;
+                case 3: hot8_run<3, false>(stage, j, jend, myz[0], Lc, Lx, acc); break;
+                case 4: hot8_run<4, false>(stage, j, jend, myz[0], Lc, Lx, acc); break;
+                case 5: hot8_run<5, false>(stage, j, jend, myz[0], Lc, Lx, acc); break;
+                case 6: hot8_run<6, false>(stage, j, jend, myz[0], Lc, Lx, acc); break;
+                default: hot8_run<7, false>(stage, j, jend, myz[0], Lc, Lx, acc); break;
+              }
+            }
+#endif
+            j = jend;
+          } else {
+            for (; j < jend; ++j) {
+              if (okv[j]) {
+#pragma unroll
+                for (int k = 0; k < ZL; ++k)
+                  acc[k] = caddf(acc[k], eval_z_fast(stage[j].eta, stage[j].co[myL[k]], myz[k]));
+              } else {
+                const int id = base + j;
+                const double w = s_wj[id];
+#pragma unroll
+                for (int k = 0; k < ZL; ++k) {
+                  cplx v = soln_literal_one(P, T, pi, s_a2[id], myz[k], mylay[k]);
+                  acc[k] = caddf(acc[k], mk(w * v.re, w * v.im));
+                }
+              }
+            }
+          }
+          const bool seg_end = (base + j == next_b && next_b < NA);
+          if (seg >= 1 && lt_ok && (seg_end || !all_ok)) {
+            // at an interval end: record its fate; inside an interval that already went
+            // non-finite for everybody (only looked at after chunks with literal nodes): stop
+            int cur_bad = 0;
+#pragma unroll
+            for (int k = 0; k < ZL; ++k) {
+              const bool f = is_finite_fastc(acc[k]);
+              if (!f) cur_bad |= 1 << k;
+              if (seg_end && f && (acc[k].re != 0.0 || acc[k].im != 0.0)) anyf |= 1 << k;
+            }
+            if (seg_end) dead |= cur_bad;
+            const int settled = (dead | cur_bad) & anyf;
+            if (__all_sync(0xffffffffu, settled == (1 << ZL) - 1)) {
+              const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+              for (int k = 0; k < ZL; ++k) {
+                if (seg_end) areas[k][seg] = acc[k];
+                for (int jj = seg_end ? seg : seg - 1; jj < nacc; ++jj) areas[k][jj + 1] = mk(nanv, nanv);
+                acc[k] = mk(nanv, nanv);
+              }
+              seg = nacc;   // the final store below rewrites series[nacc-1] with NaN
+              done = true;
+              break;
+            }
+          }
+          if (seg_end) {
+#pragma unroll
+            for (int k = 0; k < ZL; ++k) {
+              areas[k][seg] = acc[k];
+              acc[k] = mk(0.0, 0.0);
+            }
+            seg += 1;
+            next_b += G;
+          }
+        }
+        __syncwarp();
+        PROF_ADD(3);
+      }
+#pragma unroll
+      for (int k = 0; k < ZL; ++k) areas[k][seg] = acc[k];
+      const double nan = __longlong_as_double(0x7ff8000000000000LL);
+      const cplx lt = T.lt[pi];
+      int live = 0;
+#pragma unroll
+      for (int k = 0; k < ZL; ++k) {
+        bool any = false;
+        for (int j = 0; j < nacc; ++j) {
+          cplx a = areas[k][j + 1];
+          const bool fin_a = is_finite_fastc(a);
+          a = fin_a ? a * lt : mk(nan, nan);
+          areas[k][j + 1] = a;
+          if (fin_a && (a.re != 0.0 || a.im != 0.0)) any = true;  // abs(GLarea) > 0, driver.f90:209
+        }
+        if (any) live |= 1 << k;
+        else stale |= 1 << k;
+      }
+      cplx infint[ZL];
+#pragma unroll
+      for (int k = 0; k < ZL; ++k) infint[k] = mk(0.0, 0.0);
+#if defined(UNC_SKIP_WYNN)
+#pragma unroll
+      for (int k = 0; k < ZL; ++k) if (live & (1 << k)) infint[k] = areas[k][1];
+#else
+#pragma unroll
+      for (int k = 0; k < ZL; ++k) if (live & (1 << k)) infint[k] = wynn_grid(&areas[k][1], nacc);
+#endif
+#pragma unroll
+      for (int k = 0; k < ZL; ++k) {
+        cplx f = areas[k][0];
+        f = is_finite_fastc(f) ? f * lt : mk(nan, nan);
+        if (pvalid) tot[(size_t)pi * ZB + GL * k + hl] = f + infint[k];   // totlap, driver.f90:216
+      }
+#pragma unroll
+      for (int k = 0; k < ZL; ++k) if (pvalid && (stale & (1 << k))) atomicOr(&flag_cur[GL * k + hl], 1);
+      PROF_ADD(4);
+    }
+    PROF_ADD(5);
+    have_prev = have_cur;
+    prev_col = col; prev_z0 = z0; prev_nzv = nzv; prev_tD = tD;
+    buf ^= 1;
+  }
+}
+
 
 // DFMA-chain microbenchmark: 8 independent chains per thread
 __global__ void fp64_peak_kernel(double *out, int iters) {
