@@ -418,7 +418,11 @@ int launch_grid(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_
   const char *force = getenv("UNC_FORCE_KERNEL");
   const bool no4 = force && !strcmp(force, "grid2");
   const bool only4 = force && !strcmp(force, "grid4");
+#ifdef UNC_GRID8_NW
+  if (J.nz >= 96 && !no4 && !only4) return launch_grid8_nw<UNC_GRID8_NW>(dev, P, J, st);   // experiments
+#else
   if (J.nz >= 96 && !no4 && !only4) return launch_grid8_nw<8>(dev, P, J, st);
+#endif
   if (J.nz >= 96 && !no4) return launch_grid4(dev, P, J, st);
   // two z per lane (64 z per CTA) halves the per-(a,p) work per point; keep one z per lane
   // for short columns and when the larger totlap tile would not fit twice per SM

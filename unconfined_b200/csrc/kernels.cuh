@@ -454,6 +454,7 @@ __device__ __noinline__ double dehoog_lane(const DevParams &P, const cplx *f, in
   q[0] = cdiv_q(d[1], mk(0.5 * d[0].re, 0.5 * d[0].im));
   for (int i = 1; i <= n2 - 1; ++i) q[i] = cdiv_q(d[i + 1], d[i]);
   d[0] = mk(0.5 * d[0].re, 0.5 * d[0].im);
+#ifdef UNC_DEHOOG_ROWWISE
   // rows are processed in register blocks of UB entries so that the thread-local loads of a
   // block are all in flight together (the table lives in L2-backed local memory)
   constexpr int UB = 6;
@@ -499,6 +500,58 @@ __device__ __noinline__ double dehoog_lane(const DevParams &P, const cplx *f, in
       }
     }
   }
+#else
+  // q-d rhombus, R = 2 columns per sweep.  Column r (invlap.f90:80-95) needs of column r-1 only
+  // the entries i and i+1, so a sweep over i can carry R consecutive columns as a software
+  // pipeline in registers: stage s turns the stream (q(i,r), e(i,r-1)) into (q(i,r+1), e(i,r))
+  // with a lag of two entries, reads come from the thread-local arrays once per sweep and
+  // the last stage writes behind the read position.  One load pair and one store pair per
+  // entry and SWEEP instead of three of each per entry and COLUMN: the table lives in
+  // L2-backed local memory and those round trips were what the inversion cost.  Stage s+1
+  // consumes what stage s produced on the previous step (pipeline registers), so the R
+  // stage updates of a step are independent instruction streams.
+  {
+#ifndef UNC_DEHOOG_R
+#define UNC_DEHOOG_R 2   // measured on C5a (ms/step): column-wise 114.9, R=2 112.5, R=3 114.4, R=4 117.9 (spills)
+#endif
+    constexpr int R = UNC_DEHOOG_R;
+    for (int r0 = 1; r0 <= M; r0 += R) {
+      const int ns = min(R, M - r0 + 1);
+      const int Lq0 = 2 * (M - r0) + 1;          // last q index of column r0
+      cplx qprev[R], eprev[R], inq[R], ine[R];
+#pragma unroll
+      for (int s2 = 0; s2 < R; ++s2) { qprev[s2] = eprev[s2] = inq[s2] = ine[s2] = mk(0.0, 0.0); }
+      const int tend = Lq0 + 3 * (ns - 1);
+      for (int tk = 0; tk <= tend; ++tk) {
+        cplx outq[R], oute[R];
+        if (tk <= Lq0) { inq[0] = q[tk]; ine[0] = e[tk]; }
+#pragma unroll
+        for (int s2 = 0; s2 < R; ++s2) {
+          outq[s2] = oute[s2] = mk(0.0, 0.0);
+          const int j = tk - 3 * s2;
+          if (s2 < ns && j >= 0 && j <= Lq0 - 2 * s2) {
+            const int r = r0 + s2;
+            const cplx qi = inq[s2], ei = ine[s2];
+            if (j == 0) d[2 * r - 1] = -qi;
+            if (j >= 1) {
+              const cplx eo = qi - qprev[s2] + ei;        // e(j-1, r)
+              if (j == 1) d[2 * r] = -eo;
+              if (j >= 2) {
+                const cplx qo = cdiv_q(qprev[s2] * eo, eprev[s2]);   // q(j-2, r+1)
+                if (s2 == ns - 1) { q[j - 2] = qo; e[j - 2] = eprev[s2]; }
+                else { outq[s2] = qo; oute[s2] = eprev[s2]; }
+              }
+              eprev[s2] = eo;
+            }
+            qprev[s2] = qi;
+          }
+        }
+#pragma unroll
+        for (int s2 = 0; s2 + 1 < R; ++s2) { inq[s2 + 1] = outq[s2]; ine[s2 + 1] = oute[s2]; }
+      }
+    }
+  }
+#endif
   double sn, cs;
   sincos_g((PI * t) / tee, &sn, &cs);
   const cplx zz = mk(cs, sn);
