@@ -124,3 +124,38 @@ def test_grid4_equals_grid2_kernel_bitwise_semantics(c5a):
     ok = np.isfinite(s2) & np.isfinite(s4)
     rel = np.abs(s4[ok] - s2[ok]) / np.maximum(np.abs(s2[ok]), 1e-300)
     assert np.median(rel) < 1e-12 and (rel < 1e-7).mean() > 0.98
+
+
+def test_grid8_equals_grid4_on_odd_column_counts_and_ragged_z(c5a):
+    """lh_grid8_kernel (8 z-slots per lane, two Laplace parameters per warp) against
+    lh_grid4_kernel on shapes that exercise its edges: odd numbers of columns, z-blocks that
+    are not full, a second partial z-block."""
+    g = c5a
+    for nr, nt, zsel in ((5, 1, slice(0, 128)), (3, 3, slice(0, 100)), (2, 1, slice(0, 128, 1))):
+        tD, sv = g["tD"][2:2 + nt], g["sv"][2:2 + nt]
+        rD = g["rD"][100:100 + 37 * nr:37]
+        zD, lay = g["zD"][zsel], g["lay"][zsel]
+        s8, d8, f8 = ub.eval_grid(g["prm"], tD, sv, rD, zD, lay, want_flags=True)
+        os.environ["UNC_FORCE_KERNEL"] = "grid4"
+        try:
+            s4, d4, f4 = ub.eval_grid(g["prm"], tD, sv, rD, zD, lay, want_flags=True)
+        finally:
+            os.environ.pop("UNC_FORCE_KERNEL", None)
+        assert np.array_equal(f8, f4)
+        assert np.array_equal(np.isnan(s8), np.isnan(s4))
+        ok = np.isfinite(s4)
+        rel = np.abs(s8[ok] - s4[ok]) / np.maximum(np.abs(s4[ok]), 1e-300)
+        assert np.median(rel) < 1e-12 and (rel < 1e-7).mean() > 0.98, (nr, nt, np.median(rel))
+    # 200 z = one full and one partial z-block, equally spaced; against the point kernel
+    z = np.linspace(0.0, 1.0, 200)
+    lay = ub.zlay(z, g["p"]["lD"], g["p"]["dD"])
+    tD, sv, rD = g["tD"][4:5], g["sv"][4:5], g["rD"][300:303]
+    s8, d8 = ub.eval_grid(g["prm"], tD, sv, rD, z, lay)
+    os.environ["UNC_FORCE_KERNEL"] = "point"
+    try:
+        sp_, dp_ = ub.eval_grid(g["prm"], tD, sv, rD, z, lay)
+    finally:
+        os.environ.pop("UNC_FORCE_KERNEL", None)
+    ok = np.isfinite(sp_)
+    rel = np.abs(s8[ok] - sp_[ok]) / np.maximum(np.abs(sp_[ok]), 1e-300)
+    assert np.median(rel) < 1e-12 and (rel < 1e-6).mean() > 0.98
