@@ -574,7 +574,8 @@ __device__ __noinline__ double dehoog_lane(const DevParams &P, const cplx *f, in
 // otherwise): blocked column order without the in-column early exit (wynn_blk) 123.4; plain
 // column order (wynn_dev) 125.6; epsilon table in registers in anti-diagonal order
 // (wynn_reg<12>: no local memory but one serial dependency chain) ~+15%; four series in
-// lockstep over local memory +6%.  UNC_WYNN_REG / UNC_WYNN_PLAIN select the others.
+// lockstep over local memory +6%; single-array anti-diagonal table in the warp's shared-memory
+// stage (no local memory at all) +1.6%.  UNC_WYNN_REG / UNC_WYNN_PLAIN select the others.
 __device__ __noinline__ cplx wynn_grid(const cplx *series, int nacc) {
 #ifdef UNC_WYNN_REG
   if (nacc <= 12) return wynn_reg<12>(series, nacc);
