@@ -332,7 +332,7 @@ def run_ours(args, rank, world, local_rank):
                                  "source": "profiles/r01_ncu_grid8_v17_summary.json (flop count from ncu, time from this run)"},
                              "traffic_note": "DRAM bytes per launch scaled from the ncu capture (51 KB/point: "
                                              "L2-evicted local memory of the de Hoog/Wynn tables; algorithmic "
-                                             "bytes are 16 B/point); 5% of HBM bandwidth, the bound is FP64",
+                                             "bytes are 16 B/point); 7% of HBM bandwidth, the bound is FP64",
                              "peak_source": "DFMA-chain microbenchmark measured in this run "
                                             "(MEASURED_PEAKS.json has no FP64 entry); nominal 37.2"},
                 "cpu_baseline": cpu}

@@ -181,3 +181,54 @@ def test_multi_gpu_sharding_is_invariant():
     sb, _ = ub.eval_grid(prm, d["tD"], d["sv"], d["rD"][11:], d["zD"], d["zLay"], ts_scale=None)
     assert np.array_equal(np.concatenate([sa, sb], axis=1), s1, equal_nan=True)
     assert n >= 1
+
+
+GRID_DECKS = ["theis-input.dat", "hantush-input.dat", "hantush-storage-input.dat", "cape-cod-moench.in",
+              "malama-fullpen-input.dat", "malama-partpen-input.dat", "mishra-neuman-malama.in"]
+
+
+@pytest.mark.parametrize("name", GRID_DECKS)
+def test_every_model_through_the_128z_grid_kernels(name):
+    """Models 0-6 through lh_grid8_kernel / lh_grid4_kernel (nz >= 96): z-lists that stay in one
+    layer, straddle one layer boundary in one slot, and cross both boundaries; checked against
+    the point kernel (itself held to the oracle on the decks above) and, on a sample, against
+    the oracle with its noise envelope."""
+    d, pd = load_deck(name)
+    lD, dD = pd["lD"], pd["dD"]
+    tD = np.array([d["tD"][len(d["tD"]) // 3], d["tD"][-1] if len(d["tD"]) > 1 else d["tD"][0] * 30.0])
+    sv = oracle.split_index(tD, d["j0s"])
+    pq = dict(pd, j0z=oracle.j0_zeros(max(d["j0s"]) + pd["gl_nacc"] + 1))
+    rD = np.array([0.3, 1.7, 6.0])
+    zsets = {"one layer": np.linspace(0.0, max(0.05, 0.9 * (1.0 - lD)), 128),
+             "all layers": np.linspace(0.0, 1.0, 128),
+             "two blocks": np.linspace(0.02, 0.98, 150)}
+    prm = ub.Params(pq)
+    for what, zD in zsets.items():
+        lay = oracle.zlay(zD, lD, dD)
+        res = {}
+        for kernel in (None, "grid4", "point"):
+            if kernel:
+                os.environ["UNC_FORCE_KERNEL"] = kernel
+            try:
+                res[kernel] = ub.eval_grid(prm, tD, sv, rD, zD, lay, want_flags=True)
+            finally:
+                os.environ.pop("UNC_FORCE_KERNEL", None)
+        s8, d8, f8 = res[None]
+        for other in ("grid4", "point"):
+            so, do_, fo = res[other]
+            assert np.array_equal(f8, fo), (name, what, other)
+            assert np.array_equal(np.isnan(s8), np.isnan(so)), (name, what, other)
+            ok = np.isfinite(so) & (np.abs(so) > 1e-12 * np.nanmax(np.abs(so)))
+            rel = np.abs(s8[ok] - so[ok]) / np.abs(so[ok])
+            assert np.median(rel) < 1e-11 and (rel < 1e-6).mean() > 0.97, (name, what, other, np.median(rel), rel.max())
+    # oracle on a thin sample of the "all layers" grid (every 9th z)
+    zD = zsets["all layers"]; lay = oracle.zlay(zD, lD, dD)
+    s8, d8, f8 = ub.eval_grid(prm, tD, sv, rD, zD, lay, want_flags=True)
+    sel = slice(0, 128, 9)
+    args = (tD, sv, rD, zD[sel], lay[sel])
+    so, do_, sps, spd = oracle_with_noise(oracle.Params(pq), args, nsamples=3)
+    _, _, fo = oracle.eval_grid(oracle.Params(pq), *args, carry=False)
+    assert np.array_equal(fo, f8[:, :, sel])
+    keep = fo == 0
+    mask = lambda a: np.where(keep, a, 0.0)   # noqa: E731
+    check_parity(mask(s8[:, :, sel]), mask(d8[:, :, sel]), mask(so), mask(do_), sps, spd, what=f"{name} grid8")
