@@ -604,6 +604,25 @@ __host__ __device__ inline size_t smem_bytes(int np, int nacc, int na, int ZT) {
   return (b + 15) & ~(size_t)15;
 }
 
+// Fast-path evaluation of one abscissa for the ZT z-values of a point-kernel tile, as a
+// separate function (own register allocation; the kernel around it holds the accumulators).
+template <int ZT>
+__device__ __noinline__ bool point_eval(const DevParams &P, cplx pp, cplx aux, cplx aux2, double a2v, double w,
+                                        int lay_mask, double eta_max, const double *zt, const int *lt_, int nzt,
+                                        cplx *f) {
+  cplx eta;
+  Coef co[3];
+  if (!ap_terms_fast(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, &eta, co)) return false;
+#pragma unroll
+  for (int k = 0; k < ZT; ++k)
+    if (k < nzt) {
+      const int L = lt_[k] - 1;
+      const Coef &c = (L == 0) ? co[0] : ((L == 1) ? co[1] : co[2]);
+      f[k] = eval_z_fast(eta, c, zt[k]);
+    } else f[k] = mk(0.0, 0.0);
+  return true;
+}
+
 #ifndef UNC_POINT_MINB
 #define UNC_POINT_MINB 2   // 128 registers, 16 warps per SM: C5b 481 ms vs 595 ms at 226 registers and 8 warps
 #endif
@@ -733,17 +752,8 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       if (valid) {
         const double w = s_wj[idx], a2v = s_a2[idx];
         cplx f[ZT];
-        cplx eta;
-        Coef co[3];
-        if (ap_terms_fast(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, &eta, co)) {
-#pragma unroll
-          for (int k = 0; k < ZT; ++k)
-            if (k < nzt) {
-              const int L = lt_[k] - 1;
-              const Coef &c = (L == 0) ? co[0] : ((L == 1) ? co[1] : co[2]);
-              f[k] = eval_z_fast(eta, c, zt[k]);
-            } else f[k] = mk(0.0, 0.0);
-        } else {
+        // per-abscissa evaluation as a call: 2% faster than inlined (own register allocation)
+        if (!point_eval<ZT>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f)) {
 #pragma unroll
           for (int k = 0; k < ZT; ++k)
             if (k < nzt) {
