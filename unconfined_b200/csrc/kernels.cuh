@@ -1260,6 +1260,41 @@ __device__ __noinline__ void hot8_run(const StageEnt8 *stage, int j, int jend, d
   for (int k = 0; k < 8; ++k) acc_io[k] = acc[k];
 }
 
+// A whole staged chunk in one call, segment ends included: when the abscissa that closes a
+// quadrature segment (tanh-sinh part or a J0 interval) has been added, the eight sums go to
+// areas[k][seg] and restart from zero.  seg_rel = chunk-relative index one past the last
+// abscissa of the current segment; boundaries at or beyond lim_rel (= end of the whole
+// quadrature) are left to the caller.  Returns the new segment index.  One call per chunk
+// instead of one per segment piece: the per-call cost (eight accumulators through local memory,
+// pipeline fill and drain) is paid 44 instead of ~60 times per job.
+template <int KX, bool K0Z>
+__device__ __noinline__ int hot8_chunk(const StageEnt8 *stage, int cnt, double z0, int L, int Lx,
+                                       cplx *acc_io, cplx *areas, int seg, int seg_rel, int lim_rel, int G) {
+  constexpr int AST = UNC_MAX_NACC + 1;
+  cplx acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = acc_io[k];
+  for (int j = 0; j < cnt; ++j) {
+    const StageEnt8 &e = stage[j];
+    const Coef c = e.co[L];
+    if (KX >= 0) {
+      const Coef cx = e.co[Lx];
+      eval8_scaled<KX, K0Z>(e, c, cx, z0, acc);
+    } else {
+      eval8_scaled<KX, K0Z>(e, c, c, z0, acc);
+    }
+    if (j + 1 == seg_rel && seg_rel < lim_rel) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { areas[k * AST + seg] = acc[k]; acc[k] = mk(0.0, 0.0); }
+      seg += 1;
+      seg_rel += G;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc_io[k] = acc[k];
+  return seg;
+}
+
 // The hot loop as separate functions: the persistent kernel around it keeps ~100 registers
 // of long-lived state, and inlined there the loop was compiled with address
 // rematerialisation (S2R/R2UR) and extra loads; as a call it gets its own register
@@ -2032,36 +2067,67 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
         while (j < cnt) {
           const int jend = min(cnt, next_b - base);
           if (all_ok && zuni && hot_ok) {
-            // hot loop: one exp+sincos for slot 0, complex-multiply recurrence for slots 1..3
+            // hot loop over the whole chunk (segment ends are handled inside the call)
+            const int seg0 = seg;
 #ifndef UNC_SKIP_HOT
+#define UNC_H8(KXV, KZV) seg = hot8_chunk<KXV, KZV>(stage, cnt, myz[0], Lc, Lx, acc, &areas[0][0], seg, next_b - base, NA - base, G)
             if (kx < 0) {
-              if (k0z) hot8_run<-1, true>(stage, j, jend, myz[0], Lc, Lc, acc);
-              else hot8_run<-1, false>(stage, j, jend, myz[0], Lc, Lc, acc);
+              if (k0z) UNC_H8(-1, true); else UNC_H8(-1, false);
             } else if (k0z) {
               switch (kx) {
-                case 0: hot8_run<0, true>(stage, j, jend, myz[0], Lc, Lx, acc); break;
-                case 1: hot8_run<1, true>(stage, j, jend, myz[0], Lc, Lx, acc); break;
-                case 2: hot8_run<2, true>(stage, j, jend, myz[0], Lc, Lx, acc); break;
-                case 3: hot8_run<3, true>(stage, j, jend, myz[0], Lc, Lx, acc); break;
-                case 4: hot8_run<4, true>(stage, j, jend, myz[0], Lc, Lx, acc); break;
-                case 5: hot8_run<5, true>(stage, j, jend, myz[0], Lc, Lx, acc); break;
-                case 6: hot8_run<6, true>(stage, j, jend, myz[0], Lc, Lx, acc); break;
-                default: hot8_run<7, true>(stage, j, jend, myz[0], Lc, Lx, acc); break;
+                case 0: UNC_H8(0, true); break;
+                case 1: UNC_H8(1, true); break;
+                case 2: UNC_H8(2, true); break;
+                case 3: UNC_H8(3, true); break;
+                case 4: UNC_H8(4, true); break;
+                case 5: UNC_H8(5, true); break;
+                case 6: UNC_H8(6, true); break;
+                default: UNC_H8(7, true); break;
               }
             } else {
               switch (kx) {
-                case 0: hot8_run<0, false>(stage, j, jend, myz[0], Lc, Lx, acc); break;
-                case 1: hot8_run<1, false>(stage, j, jend, myz[0], Lc, Lx, acc); break;
-                case 2: hot8_run<2, false>(stage, j, jend, myz[0], Lc, Lx, acc); break;
-                case 3: hot8_run<3, false>(stage, j, jend, myz[0], Lc, Lx, acc); break;
-                case 4: hot8_run<4, false>(stage, j, jend, myz[0], Lc, Lx, acc); break;
-                case 5: hot8_run<5, false>(stage, j, jend, myz[0], Lc, Lx, acc); break;
-                case 6: hot8_run<6, false>(stage, j, jend, myz[0], Lc, Lx, acc); break;
-                default: hot8_run<7, false>(stage, j, jend, myz[0], Lc, Lx, acc); break;
+                case 0: UNC_H8(0, false); break;
+                case 1: UNC_H8(1, false); break;
+                case 2: UNC_H8(2, false); break;
+                case 3: UNC_H8(3, false); break;
+                case 4: UNC_H8(4, false); break;
+                case 5: UNC_H8(5, false); break;
+                case 6: UNC_H8(6, false); break;
+                default: UNC_H8(7, false); break;
               }
             }
+#undef UNC_H8
+#else
+            while (next_b - base <= cnt && next_b < NA) { seg += 1; next_b += G; }
+            next_b -= (seg - seg0) * G;
 #endif
-            j = jend;
+            next_b += (seg - seg0) * G;
+            j = cnt;
+            // fate of the intervals closed inside this chunk (see the comment at `dead`)
+            if (lt_ok) {
+              for (int sidx = max(seg0, 1); sidx < seg && !done; ++sidx) {
+                int cur_bad = 0;
+#pragma unroll
+                for (int k = 0; k < ZL; ++k) {
+                  const cplx a = areas[k][sidx];
+                  const bool f = is_finite_fastc(a);
+                  if (!f) cur_bad |= 1 << k;
+                  if (f && (a.re != 0.0 || a.im != 0.0)) anyf |= 1 << k;
+                }
+                dead |= cur_bad;
+                if (__all_sync(0xffffffffu, (dead & anyf) == (1 << ZL) - 1)) {
+                  const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+                  for (int k = 0; k < ZL; ++k) {
+                    for (int jj = sidx + 1; jj <= nacc; ++jj) areas[k][jj] = mk(nanv, nanv);
+                    acc[k] = mk(nanv, nanv);
+                  }
+                  seg = nacc;   // the final store below rewrites areas[nacc] with NaN
+                  done = true;
+                }
+              }
+            }
+            continue;
           } else {
             for (; j < jend; ++j) {
               if (okv[j]) {
