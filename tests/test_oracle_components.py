@@ -223,3 +223,26 @@ def test_stale_infint_carry_matches_reference_order():
     s0, _, f0 = oracle.eval_grid(po, d["tD"], d["sv"], rD, d["zD"][:3], d["zLay"][:3], ts_scale=sc, carry=False)
     assert np.array_equal(f0, f1)
     assert np.array_equal(s0[0, 0], s1[0, 0]) and np.array_equal(s0[0, 2], s1[0, 2])
+
+
+def test_oracle_converges_to_independent_mpmath_values():
+    """Known answers from a DIFFERENT numerical route (tools/make_independent_truth.py: mpmath
+    quadosc for the Hankel integral, fixed-Talbot Laplace inversion, 30 digits) for Hantush
+    (model 1) and Neuman 1974 (model 5, beta = 0).  With the decks' own orders the reference
+    algorithm is ~1e-3..1e-4 accurate (tanh-sinh k=7 / k=6 on the first J0 interval, SURVEY P1);
+    refining the tanh-sinh rule must bring the oracle to the algorithm's 3e-5 floor of them."""
+    import json
+    truth = json.load(open(os.path.join(ROOT, "tests", "golden", "independent_mpmath.json")))
+    assert len(truth) >= 3
+    for t in truth:
+        d, pd = load_deck(t["deck"])
+        it = t["time_index"]
+        assert abs(d["tD"][it] - t["tD"]) < 1e-12 * t["tD"]
+        err = {}
+        for tag, kw in (("deck", {}), ("fine", dict(ts_k=9, ts_R=7))):
+            q = dict(pd, **kw)
+            s, _, _ = oracle.eval_grid(oracle.Params(q), d["tD"][it:it + 1], d["sv"][it:it + 1], d["rD"],
+                                       d["zD"][:1], d["zLay"][:1], carry=False)
+            err[tag] = abs(s.ravel()[0] - t["s_D"]) / t["s_D"]
+        assert err["deck"] < 2e-3, (t["deck"], err)
+        assert err["fine"] < 5e-5 and err["fine"] < err["deck"], (t["deck"], err)
