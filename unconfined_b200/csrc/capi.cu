@@ -384,6 +384,9 @@ int launch_grid8_nw(int dev, const unc::DevParams &P, const unc::Job &J, cudaStr
   DevCtx &c = g_ctx[dev];
   if (!c.smem_set[20]) {
     CK(cudaFuncSetAttribute(unc::lh_grid8_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#ifdef UNC_CARVEOUT   // measured (ms/step): default 111.7 = 60 (132 KB shared, 124 KB L1); 100 (28 KB L1) 115.8
+    CK(cudaFuncSetAttribute(unc::lh_grid8_kernel<NW>, cudaFuncAttributePreferredSharedMemoryCarveout, UNC_CARVEOUT));
+#endif
     c.smem_set[20] = true;
   }
   const long long nitems = J.ncol * ((J.nz + 127) / 128);
