@@ -438,6 +438,9 @@ int launch_grid(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_
 int launch(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
   const char *force = getenv("UNC_FORCE_KERNEL");
   bool grid = J.nz >= 12;
+  // a small contour grid (fewer column CTAs than SMs) is a latency problem: the point kernel
+  // spreads it over nz/4 times as many CTAs (hantush-contours deck, 30 r x 20 z: 6.9 ms -> <1 ms)
+  if (grid && J.nz < 96 && J.ncol * ((J.nz + 31) / 32) < (long long)g_ctx[dev].sm_count) grid = false;
   if (force && !strcmp(force, "point")) grid = false;
   if (force && (!strcmp(force, "grid") || !strcmp(force, "grid2") || !strcmp(force, "grid4"))) grid = true;
   if (grid) return launch_grid(dev, P, J, st);
