@@ -242,10 +242,13 @@ struct Coef {  // f(z) = k0 + cp*exp(eta z) + cm*exp(-eta z)
 // times a*J0(a rD)) is folded into the coefficients.
 //   aux  : model 3: sum_m 1/(1+p/gamma_m);  model 2: A0(p) = 2/(p CDw K0 + xi K1)
 //   aux2 : model 2: p*tDb + 1
-__host__ __device__ __forceinline__ bool ap_terms_fast(const DevParams &P, cplx p, cplx aux, cplx aux2,
-                                              double a2, double w, int lay_mask, double eta_max,
-                                              cplx *eta_out, Coef *co /* [3], indexed by layer-1 */) {
-  const int model = P.model;
+// MODEL >= 0: the model is a compile-time constant (the other models' branches vanish from the
+// instantiation: less code, fewer live values); MODEL = -1: taken from P at run time.
+template <int MODEL>
+__host__ __device__ __forceinline__ bool ap_terms_fast_t(const DevParams &P, cplx p, cplx aux, cplx aux2,
+                                                double a2, double w, int lay_mask, double eta_max,
+                                                cplx *eta_out, Coef *co /* [3], indexed by layer-1 */) {
+  const int model = (MODEL >= 0) ? MODEL : P.model;
   const cplx pa = mk(p.re + a2, p.im);
   const cplx zero = mk(0.0, 0.0);
   if (model == 0) {
@@ -340,6 +343,12 @@ __host__ __device__ __forceinline__ bool ap_terms_fast(const DevParams &P, cplx 
     }
   }
   return true;
+}
+
+__host__ __device__ __forceinline__ bool ap_terms_fast(const DevParams &P, cplx p, cplx aux, cplx aux2,
+                                              double a2, double w, int lay_mask, double eta_max,
+                                              cplx *eta_out, Coef *co) {
+  return ap_terms_fast_t<-1>(P, p, aux, aux2, a2, w, lay_mask, eta_max, eta_out, co);
 }
 
 // f(z) for one z given the per-(a,p) terms: one exp_pm + one sincos + 12 FMA

@@ -1377,11 +1377,12 @@ __device__ __noinline__ int ap_terms_stage(const DevParams &P, cplx p, cplx aux,
 }
 
 // The same for the eight-slot kernel: also exp(+-eta*Dz*kx) for the exception slot kx (>= 1).
-__device__ __noinline__ int ap_terms_stage8(const DevParams &P, cplx p, cplx aux, cplx aux2, double a2,
-                                            double w, int lay_mask, double eta_max, bool zuni,
-                                            double Dz, int kx, StageEnt8 *out) {
+template <int MODEL>
+__device__ __noinline__ int ap_terms_stage8_t(const DevParams &P, cplx p, cplx aux, cplx aux2, double a2,
+                                              double w, int lay_mask, double eta_max, bool zuni,
+                                              double Dz, int kx, StageEnt8 *out) {
   StageEnt8 e;
-  const bool ok = ap_terms_fast(P, p, aux, aux2, a2, w, lay_mask, eta_max, &e.eta, e.co);
+  const bool ok = ap_terms_fast_t<MODEL>(P, p, aux, aux2, a2, w, lay_mask, eta_max, &e.eta, e.co);
   e.sp = e.sm = e.spx = e.smx = mk(1.0, 0.0);
   if (zuni && ok) {
     const cbundle S = cexp_bundle(e.eta.re * Dz, e.eta.im * Dz);
@@ -1396,6 +1397,24 @@ __device__ __noinline__ int ap_terms_stage8(const DevParams &P, cplx p, cplx aux
   }
   *out = e;
   return ok ? 1 : 0;
+}
+
+__device__ __forceinline__ int ap_terms_stage8(const DevParams &P, cplx p, cplx aux, cplx aux2, double a2,
+                                               double w, int lay_mask, double eta_max, bool zuni,
+                                               double Dz, int kx, StageEnt8 *out) {
+#ifdef UNC_AP_RUNTIME_MODEL
+  return ap_terms_stage8_t<-1>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, out);
+#else
+  switch (P.model) {   // warp-uniform
+    case 0: return ap_terms_stage8_t<0>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, out);
+    case 1: return ap_terms_stage8_t<1>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, out);
+    case 2: return ap_terms_stage8_t<2>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, out);
+    case 3: return ap_terms_stage8_t<3>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, out);
+    case 4: return ap_terms_stage8_t<4>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, out);
+    case 5: return ap_terms_stage8_t<5>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, out);
+    default: return ap_terms_stage8_t<6>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, out);
+  }
+#endif
 }
 
 __host__ __device__ inline size_t grid8_smem_bytes(int np, int na_seq, int NW) {
