@@ -606,12 +606,13 @@ __host__ __device__ inline size_t smem_bytes(int np, int nacc, int na, int ZT) {
 
 // Fast-path evaluation of one abscissa for the ZT z-values of a point-kernel tile, as a
 // separate function (own register allocation; the kernel around it holds the accumulators).
-template <int ZT, int MODEL>
+template <int ZT, int MODEL, int LMASK>
 __device__ __noinline__ bool point_eval_t(const DevParams &P, cplx pp, cplx aux, cplx aux2, double a2v, double w,
-                                          int lay_mask, double eta_max, const double *zt, const int *lt_, int nzt,
+                                          int lay_mask_rt, double eta_max, const double *zt, const int *lt_, int nzt,
                                           cplx *f) {
   cplx eta;
   Coef co[3];
+  const int lay_mask = (LMASK > 0) ? LMASK : lay_mask_rt;   // a single z: its layer is a compile-time constant too
   if (!ap_terms_fast_t<MODEL>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, &eta, co)) return false;
 #pragma unroll
   for (int k = 0; k < ZT; ++k)
@@ -623,19 +624,31 @@ __device__ __noinline__ bool point_eval_t(const DevParams &P, cplx pp, cplx aux,
   return true;
 }
 
-// model known at compile time inside the call (see ap_terms_fast_t); the switch is warp-uniform
+// model (and, for a single z, the layer) known at compile time inside the call (see
+// ap_terms_fast_t); the switches are warp-uniform
+template <int ZT, int MODEL>
+__device__ __forceinline__ bool point_eval_m(const DevParams &P, cplx pp, cplx aux, cplx aux2, double a2v, double w,
+                                             int lay_mask, double eta_max, const double *zt, const int *lt_, int nzt,
+                                             cplx *f) {
+  if (ZT == 1) {
+    if (lay_mask == 1) return point_eval_t<ZT, MODEL, 1>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f);
+    if (lay_mask == 2) return point_eval_t<ZT, MODEL, 2>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f);
+    if (lay_mask == 4) return point_eval_t<ZT, MODEL, 4>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f);
+  }
+  return point_eval_t<ZT, MODEL, 0>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f);
+}
 template <int ZT>
 __device__ __forceinline__ bool point_eval(const DevParams &P, cplx pp, cplx aux, cplx aux2, double a2v, double w,
                                            int lay_mask, double eta_max, const double *zt, const int *lt_, int nzt,
                                            cplx *f) {
   switch (P.model) {
-    case 0: return point_eval_t<ZT, 0>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f);
-    case 1: return point_eval_t<ZT, 1>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f);
-    case 2: return point_eval_t<ZT, 2>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f);
-    case 3: return point_eval_t<ZT, 3>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f);
-    case 4: return point_eval_t<ZT, 4>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f);
-    case 5: return point_eval_t<ZT, 5>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f);
-    default: return point_eval_t<ZT, 6>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f);
+    case 0: return point_eval_m<ZT, 0>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f);
+    case 1: return point_eval_m<ZT, 1>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f);
+    case 2: return point_eval_m<ZT, 2>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f);
+    case 3: return point_eval_m<ZT, 3>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f);
+    case 4: return point_eval_m<ZT, 4>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f);
+    case 5: return point_eval_m<ZT, 5>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f);
+    default: return point_eval_m<ZT, 6>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f);
   }
 }
 
