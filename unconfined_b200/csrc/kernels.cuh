@@ -424,9 +424,10 @@ __device__ __forceinline__ cplx cdiv_q(cplx a, cplx b) {
 // with one inversion per lane the q-d table is two thread-local columns updated in place
 // (e(i,r) and q(i,r+1) only read entries at i and i+1 of the previous column).
 // deriv: invert fp*p (driver.f90:228) with p regenerated as in deHoog_pvalues.
-__device__ __noinline__ double dehoog_lane(const DevParams &P, const cplx *f, int fstride,
-                                           bool deriv, double t, double tee) {
-  const int M = P.M, n2 = 2 * M;
+template <int MT>
+__device__ __noinline__ double dehoog_lane_t(const DevParams &P, const cplx *f, int fstride,
+                                             bool deriv, double t, double tee) {
+  const int M = (MT > 0) ? MT : P.M, n2 = 2 * M;   // MT > 0: loop bounds known at compile time
   const double PI = 3.141592653589793;
   cplx q[2 * 31 + 2], e[2 * 31 + 2], d[2 * 31 + 2];
   double mx = -1.0;
@@ -568,6 +569,15 @@ __device__ __noinline__ double dehoog_lane(const DevParams &P, const cplx *f, in
   cplx B2M = Bm1 + rem * Bm2;
   const double gamma = P.alpha - P.log_tol / (2.0 * tee);
   return exp(gamma * t) / tee * (A2M / B2M).re;
+}
+
+__device__ __forceinline__ double dehoog_lane(const DevParams &P, const cplx *f, int fstride,
+                                              bool deriv, double t, double tee) {
+#ifndef UNC_DEHOOG_RUNTIME_M
+  if (P.M == 26) return dehoog_lane_t<26>(P, f, fstride, deriv, t, tee);   // the decks' values
+  if (P.M == 10) return dehoog_lane_t<10>(P, f, fstride, deriv, t, tee);
+#endif
+  return dehoog_lane_t<0>(P, f, fstride, deriv, t, tee);
 }
 
 // Wynn-epsilon for the grid kernel.  Measured alternatives (C5a, ms per step, same build
@@ -1428,6 +1438,48 @@ __device__ __noinline__ int ap_terms_stage8_t(const DevParams &P, cplx p, cplx a
   return ok ? 1 : 0;
 }
 
+// Exact per-slot evaluation of staged abscissae j..jend-1 for the eight z of a lane: the fast
+// closed form with one exponential per slot where the per-(a,p) terms exist (okv), the literal
+// path otherwise.  z, layers and the padding-slot rules are rebuilt exactly as in the kernel.
+__device__ __noinline__ void slow8_run(const DevParams &P, const PTab &T, int pi, const StageEnt8 *stage,
+                                       const int *okv, int base, int j, int jend, const double *s_wj,
+                                       const double *s_a2, const double *zsrc, const int *lsrc, int nzv,
+                                       int hl, int L0, bool zuni, double Dz, cplx *acc) {
+  double myz[8];
+  int mylay[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int zi = hl + 16 * k;
+    const bool v = zi < nzv;
+    myz[k] = v ? zsrc[zi] : 0.0;
+    mylay[k] = v ? lsrc[zi] : 0;
+  }
+  const bool v0 = hl < nzv;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (!(hl + 16 * k < nzv)) {
+      mylay[k] = L0 + 1;
+      myz[k] = zuni ? myz[0] + k * Dz : 0.5;
+      if (!v0) myz[k] = 0.5;
+    }
+  }
+  for (; j < jend; ++j) {
+    if (okv[j]) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        acc[k] = caddf(acc[k], eval_z_fast(stage[j].eta, stage[j].co[mylay[k] - 1], myz[k]));
+    } else {
+      const int id = base + j;
+      const double w = s_wj[id];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        cplx v = soln_literal_one(P, T, pi, s_a2[id], myz[k], mylay[k]);
+        acc[k] = caddf(acc[k], mk(w * v.re, w * v.im));
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ int ap_terms_stage8(const DevParams &P, cplx p, cplx aux, cplx aux2, double a2,
                                                double w, int lay_mask, double eta_max, bool zuni,
                                                double Dz, int kx, StageEnt8 *out) {
@@ -2177,21 +2229,12 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
             }
             continue;
           } else {
-            for (; j < jend; ++j) {
-              if (okv[j]) {
-#pragma unroll
-                for (int k = 0; k < ZL; ++k)
-                  acc[k] = caddf(acc[k], eval_z_fast(stage[j].eta, stage[j].co[myL[k]], myz[k]));
-              } else {
-                const int id = base + j;
-                const double w = s_wj[id];
-#pragma unroll
-                for (int k = 0; k < ZL; ++k) {
-                  cplx v = soln_literal_one(P, T, pi, s_a2[id], myz[k], mylay[k]);
-                  acc[k] = caddf(acc[k], mk(w * v.re, w * v.im));
-                }
-              }
-            }
+            // rare: abscissae beyond the fast-path bound, z-lists that are not equally spaced,
+            // more than one slot off the common layer -- kept out of line (and re-reading its
+            // z from global memory) so that it does not weigh on the registers of the common path
+            slow8_run(P, T, pi, stage, okv, base, j, jend, s_wj, s_a2, J.zD + zbase, J.zLay + zbase, nzv, hl,
+                      L0, zuni, Dz, acc);
+            j = jend;
           }
           const bool seg_end = (base + j == next_b && next_b < NA);
           if (seg >= 1 && lt_ok && (seg_end || !all_ok)) {

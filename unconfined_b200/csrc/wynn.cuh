@@ -48,8 +48,9 @@ __host__ __device__ __noinline__ cplx wynn_dev(const cplx *series, int nacc) {
 // the later entries of that column hold no longer matters) and in blocks of four rows whose
 // loads are issued together: the table lives in L2-backed local memory and one dependent
 // round trip per entry is what the plain loop costs.
-__host__ __device__ __noinline__ cplx wynn_blk(const cplx *series, int nacc) {
-  cplx X[UNC_MAX_NACC + 4], Y[UNC_MAX_NACC + 4];  // 1-based; X: odd columns (starts as col -1), Y: even
+template <int NMAX>
+__host__ __device__ __noinline__ cplx wynn_blk_t(const cplx *series, int nacc) {
+  cplx X[NMAX + 4], Y[NMAX + 4];  // 1-based; X: odd columns (starts as col -1), Y: even
   int ns = nacc;
   cplx run = mk(0.0, 0.0);
   for (int i = 1; i <= nacc; ++i) {
@@ -94,6 +95,13 @@ __host__ __device__ __noinline__ cplx wynn_blk(const cplx *series, int nacc) {
     if (hit) return ret;
   }
   return Y[2];
+}
+
+__host__ __device__ __forceinline__ cplx wynn_blk(const cplx *series, int nacc) {
+#ifdef UNC_WYNN_SMALL
+  if (nacc <= 12) return wynn_blk_t<12>(series, nacc);   // smaller thread-local columns
+#endif
+  return wynn_blk_t<UNC_MAX_NACC>(series, nacc);
 }
 
 // The same algorithm with the epsilon table held in REGISTERS (north_star): anti-diagonal
