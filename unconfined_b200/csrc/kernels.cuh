@@ -1438,6 +1438,89 @@ __device__ __noinline__ int ap_terms_stage8_t(const DevParams &P, cplx p, cplx a
   return ok ? 1 : 0;
 }
 
+// Per-item tables, built by the whole CTA (kept out of line: once per item, not on the
+// per-abscissa path): de Hoog p (invlap.f90:166-170), lapTime(p), the Moench sum / wellbore
+// storage factors, and per abscissa a^2 and weight*a*J0(a rD).
+__device__ __noinline__ void item_tables(const DevParams &P, const PTab &T, double *s_a2, double *s_wj, double tD,
+                                         int sv, double rD, double tscale, int tid, int nthreads) {
+  const int np = P.np, nacc = P.nacc, G = P.G, N = P.N;
+  const int NA = N + nacc * G;
+  const int na_seq = (NA + 31) & ~31;
+  const double tee = P.tee_mult * tD;
+  const double arg = P.j0z[sv - 1] / rD;                      // driver.f90:120
+  for (int i = tid; i < np; i += nthreads) {
+    const double PI = 3.141592653589793;
+    double sigma = P.alpha - P.log_tol / (2.0 * tee);   // invlap.f90:166-170
+    cplx p = mk(sigma, PI * (double)i / tee);
+    T.p[i] = p;
+    T.lt[i] = laptime_dev(P, p);
+    cplx aux = mk(0.0, 0.0), aux2 = mk(0.0, 0.0);
+    if (P.model == 3) {
+      for (int m = 0; m < P.moench_M; ++m) aux = aux + 1.0 / (1.0 + p * (1.0 / P.moench_gamma[m]));
+    } else if (P.model == 2) {
+      cplx xi = P.rDw * csqrt_g(p);
+      cplx K[2];
+      cbesk01_dev(xi, K);
+      aux = 2.0 / (p * P.CDw * K[0] + xi * K[1]);
+      aux2 = p * P.tDb + 1.0;
+    }
+    T.aux[i] = aux;
+    T.aux2[i] = aux2;
+  }
+  for (int idx = tid; idx < na_seq; idx += nthreads) {
+    double a = 0.0, w = 0.0;
+    if (idx < N) {
+      a = (P.ts_T[idx] * tscale) / 2.0;  // integration.f90:62
+      w = P.ts_wc[idx] * (arg / 2.0);    // driver.f90:135,154 + Richardson (linear in tmp)
+    } else if (idx < NA) {
+      const int node = idx - N;
+      const int j = node / G, m = node - j * G;
+      const double lob = P.j0z[sv + j - 1] / rD;  // driver.f90:188-193
+      const double hib = P.j0z[sv + j] / rD;
+      const double width = hib - lob;
+      a = fma(width, P.gl_x[m], hib + lob) / 2.0;
+      w = P.gl_w[m] * (width / 2.0);
+    }
+    s_a2[idx] = a * a;
+    s_wj[idx] = (w != 0.0) ? w * (a * j0_dev(a * rD)) : 0.0;  // laplace_hankel_solutions.f90:118
+  }
+}
+
+// End of a p-job for the eight slots of a lane (kept out of line: it is not part of the
+// per-abscissa path and its loops would otherwise weigh on the kernel's register allocation):
+// areas[k][0] = finite part, areas[k][1..nacc] = interval areas, both still without lapTime.
+// Applies lapTime (laplace_hankel_solutions.f90:118), runs Wynn-epsilon where some area is
+// finite and non-zero (driver.f90:209; otherwise infint = 0 and the slot is flagged stale),
+// stores totlap = finint + infint (driver.f90:216) at out[16 k] unless out is null.
+__device__ __noinline__ int finish8(cplx *areas, int nacc, cplx lt, cplx *out) {
+  constexpr int AST = UNC_MAX_NACC + 1;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  int stale = 0;
+  for (int k = 0; k < 8; ++k) {
+    cplx *ar = areas + k * AST;
+    bool any = false;
+    for (int j = 1; j <= nacc; ++j) {
+      cplx a = ar[j];
+      const bool fin_a = is_finite_fastc(a);
+      a = fin_a ? a * lt : mk(nan, nan);
+      ar[j] = a;
+      if (fin_a && (a.re != 0.0 || a.im != 0.0)) any = true;  // abs(GLarea) > 0, driver.f90:209
+    }
+    cplx infint = mk(0.0, 0.0);
+    if (any) {
+#if defined(UNC_SKIP_WYNN)
+      infint = ar[1];
+#else
+      infint = wynn_grid(ar + 1, nacc);
+#endif
+    } else stale |= 1 << k;
+    cplx f = ar[0];
+    f = is_finite_fastc(f) ? f * lt : mk(nan, nan);
+    if (out) out[16 * k] = f + infint;
+  }
+  return stale;
+}
+
 // Exact per-slot evaluation of staged abscissae j..jend-1 for the eight z of a lane: the fast
 // closed form with one exponential per slot where the per-(a,p) terms exist (okv), the literal
 // path otherwise.  z, layers and the padding-slot rules are rebuilt exactly as in the kernel.
@@ -2000,42 +2083,7 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
     // ---- prologue (tables of the current item) -----------------------------------
     if (have_cur) {
       if (tid < ZB) flag_cur[tid] = 0;
-      for (int i = tid; i < np; i += NW * 32) {
-        const double PI = 3.141592653589793;
-        double sigma = P.alpha - P.log_tol / (2.0 * tee);   // invlap.f90:166-170
-        cplx p = mk(sigma, PI * (double)i / tee);
-        T.p[i] = p;
-        T.lt[i] = laptime_dev(P, p);
-        cplx aux = mk(0.0, 0.0), aux2 = mk(0.0, 0.0);
-        if (P.model == 3) {
-          for (int m = 0; m < P.moench_M; ++m) aux = aux + 1.0 / (1.0 + p * (1.0 / P.moench_gamma[m]));
-        } else if (P.model == 2) {
-          cplx xi = P.rDw * csqrt_g(p);
-          cplx K[2];
-          cbesk01_dev(xi, K);
-          aux = 2.0 / (p * P.CDw * K[0] + xi * K[1]);
-          aux2 = p * P.tDb + 1.0;
-        }
-        T.aux[i] = aux;
-        T.aux2[i] = aux2;
-      }
-      for (int idx = tid; idx < na_seq; idx += NW * 32) {
-        double a = 0.0, w = 0.0;
-        if (idx < N) {
-          a = (P.ts_T[idx] * tscale) / 2.0;  // integration.f90:62
-          w = P.ts_wc[idx] * (arg / 2.0);    // driver.f90:135,154 + Richardson (linear in tmp)
-        } else if (idx < NA) {
-          const int node = idx - N;
-          const int j = node / G, m = node - j * G;
-          const double lob = P.j0z[sv + j - 1] / rD;  // driver.f90:188-193
-          const double hib = P.j0z[sv + j] / rD;
-          const double width = hib - lob;
-          a = fma(width, P.gl_x[m], hib + lob) / 2.0;
-          w = P.gl_w[m] * (width / 2.0);
-        }
-        s_a2[idx] = a * a;
-        s_wj[idx] = (w != 0.0) ? w * (a * j0_dev(a * rD)) : 0.0;  // laplace_hankel_solutions.f90:118
-      }
+      item_tables(P, T, s_a2, s_wj, tD, sv, rD, tscale, tid, NW * 32);
       if (warp == 0) {
         int m = 0;
         float za = 0.f;
@@ -2277,38 +2325,8 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       }
 #pragma unroll
       for (int k = 0; k < ZL; ++k) areas[k][seg] = acc[k];
-      const double nan = __longlong_as_double(0x7ff8000000000000LL);
-      const cplx lt = T.lt[pi];
-      int live = 0;
-#pragma unroll
-      for (int k = 0; k < ZL; ++k) {
-        bool any = false;
-        for (int j = 0; j < nacc; ++j) {
-          cplx a = areas[k][j + 1];
-          const bool fin_a = is_finite_fastc(a);
-          a = fin_a ? a * lt : mk(nan, nan);
-          areas[k][j + 1] = a;
-          if (fin_a && (a.re != 0.0 || a.im != 0.0)) any = true;  // abs(GLarea) > 0, driver.f90:209
-        }
-        if (any) live |= 1 << k;
-        else stale |= 1 << k;
-      }
-      cplx infint[ZL];
-#pragma unroll
-      for (int k = 0; k < ZL; ++k) infint[k] = mk(0.0, 0.0);
-#if defined(UNC_SKIP_WYNN)
-#pragma unroll
-      for (int k = 0; k < ZL; ++k) if (live & (1 << k)) infint[k] = areas[k][1];
-#else
-#pragma unroll
-      for (int k = 0; k < ZL; ++k) if (live & (1 << k)) infint[k] = wynn_grid(&areas[k][1], nacc);
-#endif
-#pragma unroll
-      for (int k = 0; k < ZL; ++k) {
-        cplx f = areas[k][0];
-        f = is_finite_fastc(f) ? f * lt : mk(nan, nan);
-        if (pvalid) tot[(size_t)pi * ZB + GL * k + hl] = f + infint[k];   // totlap, driver.f90:216
-      }
+      // lapTime, Wynn-epsilon on the interval areas, totlap = finint + infint for the 8 slots
+      stale = finish8(&areas[0][0], nacc, T.lt[pi], pvalid ? tot + (size_t)pi * ZB + hl : nullptr);
 #pragma unroll
       for (int k = 0; k < ZL; ++k) if (pvalid && (stale & (1 << k))) atomicOr(&flag_cur[GL * k + hl], 1);
       PROF_ADD(4);
