@@ -69,10 +69,12 @@ __host__ __device__ __forceinline__ bool is_finite_c(cplx z) {
   return !(isnan(a) || a > DBL_MAX);
 }
 
-// same predicate without the hypot call when both components are far from overflow
+// same predicate without the hypot call when both components are far from overflow; the rare
+// rest goes through a real call (hypot is ~100 instructions, and this sits in many unrolled loops)
+__host__ __device__ __noinline__ bool is_finite_slowc(cplx z) { return is_finite_c(z); }
 __host__ __device__ __forceinline__ bool is_finite_fastc(cplx z) {
   if (fabs(z.re) < 1e150 && fabs(z.im) < 1e150) return true;   // false for NaN
-  return is_finite_c(z);
+  return is_finite_slowc(z);
 }
 
 // ---- glibc-shaped complex elementary functions (finite arguments) ----------
