@@ -1499,12 +1499,20 @@ __device__ __noinline__ int finish8(cplx *areas, int nacc, cplx lt, cplx *out) {
   for (int k = 0; k < 8; ++k) {
     cplx *ar = areas + k * AST;
     bool any = false;
-    for (int j = 1; j <= nacc; ++j) {
-      cplx a = ar[j];
-      const bool fin_a = is_finite_fastc(a);
-      a = fin_a ? a * lt : mk(nan, nan);
-      ar[j] = a;
-      if (fin_a && (a.re != 0.0 || a.im != 0.0)) any = true;  // abs(GLarea) > 0, driver.f90:209
+    for (int j0 = 1; j0 <= nacc; j0 += 4) {       // four thread-local loads in flight at a time
+      cplx v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ar[min(j0 + u, nacc)];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (j0 + u <= nacc) {
+          cplx a = v[u];
+          const bool fin_a = is_finite_fastc(a);
+          a = fin_a ? a * lt : mk(nan, nan);
+          ar[j0 + u] = a;
+          if (fin_a && (a.re != 0.0 || a.im != 0.0)) any = true;  // abs(GLarea) > 0, driver.f90:209
+        }
+      }
     }
     cplx infint = mk(0.0, 0.0);
     if (any) {
