@@ -201,7 +201,7 @@ def test_device_wynn_matches_oracle_including_edge_semantics(hc):
     for s in cases:
         want, info = oracle.wynn(s)
         n_cancel += info == 3
-        for which in (0, 1, 2, 3):
+        for which in (0, 1, 2, 3, 4):
             got = _hc_wynn(hc, s, which)
             assert abs(got - want) <= 1e-12 * max(abs(want), 1e-300) + 1e-300, (which, info, s, got, want)
     assert n_cancel >= 5        # the early-exit branch was really exercised

@@ -584,8 +584,10 @@ __device__ __forceinline__ double dehoog_lane(const DevParams &P, const cplx *f,
 // otherwise): blocked column order without the in-column early exit (wynn_blk) 123.4; plain
 // column order (wynn_dev) 125.6; epsilon table in registers in anti-diagonal order
 // (wynn_reg<12>: no local memory but one serial dependency chain) ~+15%; four series in
-// lockstep over local memory +6%; single-array anti-diagonal table in the warp's shared-memory
-// stage (no local memory at all) +1.6%.  UNC_WYNN_REG / UNC_WYNN_PLAIN select the others.
+// lockstep over local memory +6%.  UNC_WYNN_REG / UNC_WYNN_PLAIN select the others.  The grid8
+// kernel keeps the table of nacc <= 14 terms in the warp's idle shared-memory stage instead
+// (wynn_loz via finish8): +1.6% when first tried, -3.9% (94.7 -> 91.0 ms) once the kernel body
+// had been slimmed down -- the same change, a different register allocation around it.
 __device__ __noinline__ cplx wynn_grid(const cplx *series, int nacc) {
 #ifdef UNC_WYNN_REG
   if (nacc <= 12) return wynn_reg<12>(series, nacc);
@@ -1492,7 +1494,7 @@ __device__ __noinline__ void item_tables(const DevParams &P, const PTab &T, doub
 // Applies lapTime (laplace_hankel_solutions.f90:118), runs Wynn-epsilon where some area is
 // finite and non-zero (driver.f90:209; otherwise infint = 0 and the slot is flagged stale),
 // stores totlap = finint + infint (driver.f90:216) at out[16 k] unless out is null.
-__device__ __noinline__ int finish8(cplx *areas, int nacc, cplx lt, cplx *out) {
+__device__ __noinline__ int finish8(cplx *areas, int nacc, cplx lt, cplx *out, cplx *wscr) {
   constexpr int AST = UNC_MAX_NACC + 1;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
   int stale = 0;
@@ -1519,7 +1521,9 @@ __device__ __noinline__ int finish8(cplx *areas, int nacc, cplx lt, cplx *out) {
 #if defined(UNC_SKIP_WYNN)
       infint = ar[1];
 #else
-      infint = wynn_grid(ar + 1, nacc);
+      // wscr: this lane's column of the warp's (now idle) stage, [table column][32 lanes]
+      if (wscr && nacc <= 14) infint = wynn_loz(ar + 1, nacc, wscr, 32);
+      else infint = wynn_grid(ar + 1, nacc);
 #endif
     } else stale |= 1 << k;
     cplx f = ar[0];
@@ -2334,7 +2338,13 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
 #pragma unroll
       for (int k = 0; k < ZL; ++k) areas[k][seg] = acc[k];
       // lapTime, Wynn-epsilon on the interval areas, totlap = finint + infint for the 8 slots
-      stale = finish8(&areas[0][0], nacc, T.lt[pi], pvalid ? tot + (size_t)pi * ZB + hl : nullptr);
+#ifndef UNC_WYNN_LOCALMEM
+      stale = finish8(&areas[0][0], nacc, T.lt[pi], pvalid ? tot + (size_t)pi * ZB + hl : nullptr,
+                      (cplx *)(s_stage + warp * 32) + lane);
+      __syncwarp();   // the scratch becomes the stage of the next job again
+#else
+      stale = finish8(&areas[0][0], nacc, T.lt[pi], pvalid ? tot + (size_t)pi * ZB + hl : nullptr, nullptr);
+#endif
 #pragma unroll
       for (int k = 0; k < ZL; ++k) if (pvalid && (stale & (1 << k))) atomicOr(&flag_cur[GL * k + hl], 1);
       PROF_ADD(4);

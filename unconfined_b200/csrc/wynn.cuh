@@ -104,6 +104,48 @@ __host__ __device__ __forceinline__ cplx wynn_blk(const cplx *series, int nacc) 
   return wynn_blk_t<UNC_MAX_NACC>(series, nacc);
 }
 
+// Anti-diagonal ("moving lozenge") order with ONE column-indexed array D[j*stride], meant for
+// shared memory: D[j] = eps(n-j, j) of the last completed anti-diagonal n.  Exit semantics as
+// wynn_reg: the reference returns at the first |denom| <= epsilon in (column, row) order, which
+// in this order is the cancel with the smallest column seen, earlier rows first; once a cancel
+// is known only smaller columns still matter (jlim).
+__host__ __device__ __forceinline__ cplx wynn_loz(const cplx *series, int nacc, cplx *D, int stride) {
+  int ns = nacc;
+  for (int i = 0; i < nacc; ++i)
+    if (!is_finite_fastc(series[i])) { ns = i; break; }
+  if (ns < nacc && ns < 4) return mk(-999999.875, 0.0);  // real(4) literal -999999.9
+  const double eps2 = 2.220446049250313e-16 * 2.220446049250313e-16;
+  cplx run = mk(0.0, 0.0), best = mk(0.0, 0.0), keep_odd = mk(0.0, 0.0);
+  int jlim = 1 << 30;  // no cancel seen yet
+  for (int n = 1; n <= ns; ++n) {
+    const cplx term = series[n - 1];
+    run = mk(run.re + term.re, run.im + term.im);   // eps(n,0) = sum(series(1:n))
+    cplx cur = run;
+    cplx pm1 = mk(0.0, 0.0);                          // eps(:,-1) = 0
+    const int jtop = min(n - 2, jlim - 1);
+    for (int j = 0; j <= jtop; ++j) {
+      const cplx a = D[j * stride];                   // eps(n-1-j, j)
+      if (n == ns && j == ns - 3) keep_odd = a;       // eps(2, ns-3)
+      D[j * stride] = cur;                            // eps(n-j, j)
+      const double dr = cur.re - a.re, di = cur.im - a.im;
+      const double n2 = fma(dr, dr, di * di);         // abs(denom) > epsilon(1.0)
+      if (n2 > eps2) {
+        const double inv = rcp_fast(n2);
+        cur = mk(fma(dr, inv, pm1.re), fma(-di, inv, pm1.im));   // eps(n-j-1, j+1)
+        pm1 = a;
+      } else {
+        best = cur;                                   // the reference returns eps(m+1, j)
+        jlim = j;
+        break;
+      }
+    }
+    if (n - 1 < jlim) D[(n - 1) * stride] = cur;
+  }
+  if (jlim < (1 << 30)) return best;
+  if (ns & 1) return keep_odd;
+  return D[(ns - 2) * stride];
+}
+
 // The same algorithm with the epsilon table held in REGISTERS (north_star): anti-diagonal
 // ("moving lozenge") order needs only one entry per column, D[j] = eps(n-j, j) of the last
 // completed anti-diagonal n, instead of two full columns in local memory (which misses L1
