@@ -304,7 +304,7 @@ def run_ours(args, rank, world, local_rank):
         # forms, scaled z-recurrences, early stop), so frac can exceed 1 while the pipe is ~50% busy.
         ncu = None
         try:
-            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_grid8_v33_summary.json")))
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_grid8_v38_summary.json")))
         except Exception:  # noqa: BLE001
             pass
         traffic = ncu["dram_bytes_per_point"] * npts if ncu else None
@@ -329,10 +329,10 @@ def run_ours(args, rank, world, local_rank):
                                  "flop_per_point": ncu["executed_fp64_flop_per_point"],
                                  "frac_of_peak": ncu["executed_fp64_flop_per_point"] * npts / (ms_per_step * 1e-3) / peak,
                                  "fp64_pipe_pct_ncu": ncu["fp64_pipe_pct_of_peak_active"],
-                                 "source": "profiles/r01_ncu_grid8_v33_summary.json (flop count from ncu, time from this run)"},
-                             "traffic_note": "DRAM bytes per launch scaled from the ncu capture (51 KB/point: "
+                                 "source": "profiles/r01_ncu_grid8_v38_summary.json (flop count from ncu, time from this run)"},
+                             "traffic_note": "DRAM bytes per launch scaled from the ncu capture (44 KB/point: "
                                              "L2-evicted local memory of the de Hoog/Wynn tables; algorithmic "
-                                             "bytes are 16 B/point); 7% of HBM bandwidth, the bound is FP64",
+                                             "bytes are 16 B/point); 8% of HBM bandwidth, the bound is FP64",
                              "peak_source": "DFMA-chain microbenchmark measured in this run "
                                             "(MEASURED_PEAKS.json has no FP64 entry); nominal 37.2"},
                 "cpu_baseline": cpu}
