@@ -18,7 +18,8 @@ import unconfined_b200 as ub  # noqa: E402
 
 DECKS = ["theis-input.dat", "hantush-input.dat", "cape-cod-neuman74.in", "cape-cod-moench.in",
          "malama-partpen-input.dat", "malama-fullpen-input.dat", "hantush-storage-input.dat",
-         "hantush-fullpen-test.in", "theis-contours-input.dat", "hantush-contours-input.dat"]
+         "hantush-fullpen-test.in", "theis-contours-input.dat", "hantush-contours-input.dat",
+         "mishra-neuman-malama.in"]
 
 
 def relerr(a, b):
@@ -50,6 +51,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "parity.txt"))
     ap.add_argument("--scatter", type=int, default=256)
+    ap.add_argument("--c5a", type=int, default=1024)
     args = ap.parse_args()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     out = open(args.out, "w")
@@ -90,6 +92,37 @@ def main():
     t2 = time.time()
     report("scatter C5b", sg, dg, so, do, fg, out)
     print(f"    oracle {t1 - t0:.2f}s gpu {t2 - t1:.3f}s; flag mismatch {int((fo != fg).sum())}")
+    # random sample of the benchmark grid itself (C5a, lh_grid8_kernel) against the oracle
+    import bench
+    dd, t, r, z = bench.c5a_grid(0)
+    p, tDg, svg, rDg, zDg, layg = bench.derive(dd, t, r, z, ub)
+    sg, dg, fg = ub.eval_grid(ub.Params(p), tDg, svg, rDg, zDg, layg, want_flags=True)
+    rng = np.random.default_rng(42)
+    n = args.c5a
+    it, ir, iz = rng.integers(0, len(tDg), n), rng.integers(0, len(rDg), n), rng.integers(0, len(zDg), n)
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+    from helpers import NOISE_K, RTOL, oracle_with_noise
+    po = oracle.Params(p)
+    pts = (tDg[it], svg[it], rDg[ir], zDg[iz], layg[iz])
+    so, do, sps, spd = oracle_with_noise(po, pts, points=True, nsamples=3)
+    fo = oracle.eval_points(po, *pts)[2]
+    keep = (fo == 0) & np.isfinite(so)
+    gs, gd = sg[it, ir, iz][keep], dg[it, ir, iz][keep]
+    es = relerr(gs, so[keep]); ed = relerr(gd, do[keep])
+    ns = sps[keep] / np.maximum(np.abs(so[keep]), 1e-300); nd = spd[keep] / np.maximum(np.abs(do[keep]), 1e-300)
+    us = np.abs(gs - so[keep]) / (RTOL * np.abs(so[keep]) + NOISE_K * sps[keep] + 1e-300)
+    ud = np.abs(gd - do[keep]) / (RTOL * np.abs(do[keep]) + NOISE_K * spd[keep] + 1e-300)
+    well = NOISE_K * sps[keep] <= RTOL * np.abs(so[keep])
+    q = lambda e: " ".join(f"{np.quantile(e, x):.2e}" for x in (0.5, 0.9, 0.99, 1.0))  # noqa: E731
+    m = (f"C5a grid sample (lh_grid8_kernel) n={int(keep.sum())} of {n}, flag mismatches {int((fo != fg[it, ir, iz]).sum())}\n"
+         f"    quantiles 50/90/99/100%\n"
+         f"    |gpu-oracle|/|oracle|                          s [{q(es)}]  ds [{q(ed)}]\n"
+         f"    oracle's own noise (libm jitter, x87)/|oracle| s [{q(ns)}]  ds [{q(nd)}]\n"
+         f"    |gpu-oracle| / (1e-9|oracle| + {NOISE_K:g} noise)       s [{q(us)}]  ds [{q(ud)}]   (<= 1 is the tests' bar)\n"
+         f"    well-conditioned points ({NOISE_K:g} noise <= 1e-9|s|): {int(well.sum())}; on these |gpu-oracle|/|oracle| s [{q(es[well])}]"
+         f"  within 1e-9 outright: {float((es[well] <= 1e-9).mean()):.3f}")
+    print(m); out.write(m + "\n")
     try:
         pk = ub.measure_fp64_peak()
         n_, nominal = ub.device_info()
