@@ -15,8 +15,9 @@ t0 = time.perf_counter()
 ub.eval_grid(prm, tD, sv, rD, zD, lay)
 dt = time.perf_counter() - t0
 ub.lib().unc_debug_profile(out, 0)
-v = np.array(out[:7], float)
-names = ['barrier wait+fetch', 'prologue', 'ap_terms(stage)', 'hot loop', 'wynn/phaseB', 'pool exit', 'de Hoog']
+v = np.array(out[:11], float)
+names = ['round barrier', 'barrier after tables', 'ap_terms(stage)', 'hot loop', 'wynn/phaseB', 'pool exit', 'de Hoog',
+         'item fetch + barrier', 'z loads', 'item_tables', 'uniformity check (warp 0)']
 print('wall %.1f ms for %d points -> %.3g points/s' % (dt * 1e3, len(tD) * len(rD) * len(zD), len(tD) * len(rD) * len(zD) / dt))
 for n, x in zip(names, v):
-    print('%-18s %6.2f%%' % (n, 100 * x / v.sum()))
+    print('%-28s %6.2f%%' % (n, 100 * x / v.sum()))

@@ -1169,8 +1169,14 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
 //    the few expensive columns (literal path at small rD) do not leave SMs idle.
 #ifdef UNC_PROFILE
 __device__ unsigned long long g_prof[16];
-#define PROF_T0() long long _t0 = clock64()
-#define PROF_ADD(i) do { long long _t1 = clock64(); if (lane == 0) atomicAdd(&g_prof[i], (unsigned long long)(_t1 - _t0)); _t0 = _t1; } while (0)
+// clock read with a memory clobber: it must not be scheduled across the barriers it brackets
+__device__ __forceinline__ long long prof_clock() {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : : "memory");
+  return t;
+}
+#define PROF_T0() long long _t0 = prof_clock()
+#define PROF_ADD(i) do { long long _t1 = prof_clock(); if (lane == 0) atomicAdd(&g_prof[i], (unsigned long long)(_t1 - _t0)); _t0 = _t1; } while (0)
 #else
 #define PROF_T0()
 #define PROF_ADD(i)
@@ -2050,6 +2056,7 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       s_misc[8] = 0;
     }
     __syncthreads();
+    PROF_ADD(7);
     const long long item = (unsigned int)s_misc[3];
     const bool have_cur = item < nitems;
     if (!have_cur) dry = true;
@@ -2093,9 +2100,11 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
     }
 
     // ---- prologue (tables of the current item) -----------------------------------
+    PROF_ADD(8);
     if (have_cur) {
       if (tid < ZB) flag_cur[tid] = 0;
       item_tables(P, T, s_a2, s_wj, tD, sv, rD, tscale, tid, NW * 32);
+      PROF_ADD(9);
       if (warp == 0) {
         int m = 0;
         float za = 0.f;
@@ -2122,6 +2131,7 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
         }
       }
     }
+    PROF_ADD(10);
     __syncthreads();
     PROF_ADD(1);
     const int lay_mask = have_cur ? s_misc[0] : 1;
