@@ -40,9 +40,12 @@ extern "C" {
 #define UNC_ERR_IO (-5)          /* deck reader: cannot open / parse */
 
 /* flag bits returned per output point by the *_ex entry points */
-#define UNC_FLAG_STALE_INFINT 1  /* every Gauss-Lobatto area of some p was 0 or non-finite:
-                                    the reference would reuse infint of the previous (t,r)
-                                    (driver.f90:209-211); this library uses 0 */
+#define UNC_FLAG_STALE_INFINT 1  /* every Gauss-Lobatto area of some p was 0 or non-finite, so the
+                                    reference does not assign infint(p,z) and keeps the value of the
+                                    last (t,r) that did (driver.f90:205-214).  Grid calls in
+                                    reference-compatible mode (ts_abscissa_scale given) reproduce
+                                    that (unc_set_carry); otherwise infint = 0 is used.  The flag is
+                                    set in both cases. */
 
 /* Flattened types.f90 parameter structs (invLaplace :31, invHankel :88, GaussLobatto :98,
  * TanhSinh :117, well :131, formation :145, solution :174).  Fortran: type, bind(C). */
@@ -89,7 +92,9 @@ typedef struct unc_params {
  *                    tanh-sinh ABSCISSAE of each (t,r).  NULL = j0z(sv(t))/rD(r) (fresh).
  *                    The reference computes the abscissae only for the first (t,r)
  *                    (driver.f90:121-126,274): a bug-compatible caller passes
- *                    j0z(sv(1))/rD(1) in every entry.
+ *                    j0z(sv(1))/rD(1) in every entry.  Passing it also selects the
+ *                    reference's stale-infint carry (driver.f90:205-214, t outer / r inner
+ *                    order, 0 before the first assignment; see unc_set_carry).
  *   ngpu             number of GPUs to shard the (t,r) columns over; 0 = all visible
  *   totint, totintd  out, column-major (nz,nr,nt): dimensionless drawdown and its
  *                    log-time derivative (driver.f90:221,228)
@@ -103,7 +108,8 @@ int unc_eval_grid_ex(const unc_params *prm, int32_t nt, const double *tD, const 
                      const int32_t *zLay, const double *ts_abscissa_scale, int32_t ngpu,
                      double *totint, double *totintd, int32_t *flags /* (nz,nr,nt) or NULL */);
 
-/* Same computation for a flattened list of n independent (r,z,t) points. */
+/* Same computation for a flattened list of n independent (r,z,t) points (no carry between
+ * points: a stale infint is 0 + flag). */
 int unc_eval_points(const unc_params *prm, int64_t n, const double *tD, const int32_t *sv,
                     const double *rD, const double *zD, const int32_t *zLay,
                     const double *ts_abscissa_scale /* (n) or NULL */, int32_t ngpu, double *s,
@@ -115,8 +121,10 @@ int unc_eval_points_ex(const unc_params *prm, int64_t n, const double *tD, const
 
 /* Device-resident variants: every array pointer is a DEVICE pointer on the current
  * device (unc_set_device), work is enqueued on `stream` (a cudaStream_t, NULL = default
- * stream) and the call returns without synchronising.  unc_params and the small
- * arrays it points to stay on the host. */
+ * stream) and the call returns without synchronising -- except unc_eval_grid_device with
+ * d_ts_abscissa_scale given, whose carry post-pass reads two counters back (it synchronises
+ * `stream`).  Scratch, tables and counters are kept per stream: calls on different streams may
+ * overlap.  unc_params and the small arrays it points to stay on the host. */
 int unc_eval_grid_device(const unc_params *prm, int32_t nt, const double *d_tD,
                          const int32_t *d_sv, int32_t nr, const double *d_rD, int32_t nz,
                          const double *d_zD, const int32_t *d_zLay,
@@ -143,6 +151,9 @@ int unc_device_info(int32_t *ngpu, double *fp64_peak_flops /* nominal: SMs*64*2*
 int unc_measure_fp64_peak(double *flops); /* DFMA-chain microbenchmark on the current device */
 int unc_kernel_launch_count(int64_t *n);  /* kernels launched by this library so far */
 int unc_shutdown(void);                   /* frees cached device buffers */
+int unc_set_carry(int32_t on);            /* default 1: see UNC_FLAG_STALE_INFINT */
+int unc_debug_force_kernel(int32_t which);/* test hook: 0 auto, 1 point kernel, 2 grid kernels,
+                                             3 lanes<->z grid kernel even for nz >= 96 */
 const char *unc_last_error(void);         /* thread-local message for the last failure */
 const char *unc_version(void);
 

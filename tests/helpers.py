@@ -44,15 +44,16 @@ def check_parity(got_s, got_ds, ref_s, ref_ds, sp_s, sp_ds, what=""):
     return float(well.mean())
 
 
-def oracle_with_noise(po, fn_args, points=False, nsamples=5, **kw):
+def oracle_with_noise(po, fn_args, points=False, nsamples=5, carry=False, **kw):
     """Oracle result plus its own rounding-noise envelope per point: the larger of
     (a) the spread under <=2-ulp libm jitter (nsamples draws) and (b) the distance to the
     same algorithm run in x87 long double.  The noise is heavy-tailed (Wynn's 1/denom, the
-    q-d divisions), hence both estimates and the factor NOISE_K."""
+    q-d divisions), hence both estimates and the factor NOISE_K.  carry=True: the reference's
+    stale-infint semantics (driver.f90:205-214), columns in (t outer, r inner) order."""
     if points:
         f = lambda **k2: oracle.eval_points(po, *fn_args, **kw, **k2)  # noqa: E731
     else:
-        f = lambda **k2: oracle.eval_grid(po, *fn_args, carry=False, **kw, **k2)  # noqa: E731
+        f = lambda **k2: oracle.eval_grid(po, *fn_args, carry=carry, **kw, **k2)  # noqa: E731
     s0, d0, sp_s, sp_d = oracle.noise_envelope(f, nsamples=nsamples)
     sl, dl = f(long_double=True)[:2]
     with np.errstate(invalid="ignore"):

@@ -223,7 +223,10 @@ def test_model6_fast_path_matches_literal_formula(hc):
     worst = 0.0
     for tD in (0.05, 3.0, 1e3, 1e7):
         pv = oracle.pvalues(po, 2 * tD)
-        for a in (1e-3, 0.03, 0.7, 5.0, 40.0, 150.0):
+        # a >= 360: Re(eta) > 350, where |Delta0|^2 overflows although Delta0 does not (the fast
+        # path is accepted up to Re(eta) = 700/1.03; reachable for rD < 0.1 at kappa = 1)
+        for a in (1e-3, 0.03, 0.7, 5.0, 40.0, 150.0, 250.0, 360.0 * math.sqrt(pd["kappa"]),
+                  600.0 * math.sqrt(pd["kappa"]), 670.0 * math.sqrt(pd["kappa"])):
             for k in (0, 1, len(pv) // 2, len(pv) - 1):
                 ok, got, eta = fast_soln(hc, pd, a, complex(pv[k]), zD, lay)
                 assert ok

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def c5a():
-    os.environ.pop("UNC_FORCE_KERNEL", None)
+    ub.force_kernel(None)
     d, t, r, z = bench.c5a_grid(0)
     p, tD, sv, rD, zD, lay = bench.derive(d, t, r, z, ub)
     prm = ub.Params(p)
@@ -67,9 +67,8 @@ def test_full_grid_random_sample_against_oracle(c5a):
     so, do, sps, spd = oracle_with_noise(po, args, points=True, nsamples=2)
     _, _, fo = oracle.eval_points(po, *args)
     assert np.array_equal(fo, g["fl"][it, ir, iz])
-    keep = fo == 0
-    well = check_parity(g["s"][it, ir, iz][keep], g["ds"][it, ir, iz][keep], so[keep], do[keep],
-                        sps[keep], spd[keep], what="C5a sample")
+    # flagged points included: fresh mode uses infint = 0 on both sides
+    well = check_parity(g["s"][it, ir, iz], g["ds"][it, ir, iz], so, do, sps, spd, what="C5a sample")
     print('well-conditioned fraction of the sample:', well)
     assert well > 0.3     # a good share of the sample is well-conditioned and held to 1e-9 outright
 
@@ -105,20 +104,37 @@ def test_small_radius_columns_overflow_flow_matches_oracle(c5a):
     assert g["p"]["j0z"][-1] / g["rD"][0] / np.sqrt(g["p"]["kappa"]) > 1000.0
     args = (g["tD"][it], g["sv"][it], g["rD"][ir], g["zD"], g["lay"])
     so2, do2, sps, spd = oracle_with_noise(po, args, nsamples=3)
-    keep = fo == 0
-    mask = lambda a: np.where(keep, a, 0.0)   # noqa: E731  (flagged points: documented deviation)
-    check_parity(mask(sg), mask(dg), mask(so2), mask(do2), sps, spd, what="C5a small radii")
+    check_parity(sg, dg, so2, do2, sps, spd, what="C5a small radii")
 
 
-def test_grid4_equals_grid2_kernel_bitwise_semantics(c5a):
-    """The persistent 128-z kernel and the 64-z kernel implement the same arithmetic except
-    for the z-recurrence of the exponentials: results agree far below the parity bar."""
+def test_small_radius_columns_reference_compatible_mode_with_carry(c5a):
+    """The benchmarked kernel in the reference's own mode: stale tanh-sinh abscissae
+    (driver.f90:121-126) and the stale-infint carry (driver.f90:205-214) over a sub-grid whose
+    smallest radii overflow, preceded and followed by healthy columns, two times.  Every point
+    is compared with oracle.eval_grid(carry=True); nothing is masked."""
     g = c5a
-    os.environ["UNC_FORCE_KERNEL"] = "grid2"
+    ir = np.array([40, 0, 1, 300, 2, 5, 3])
+    it = np.array([1, 6])
+    tD, sv, rD = g["tD"][it], g["sv"][it], g["rD"][ir]
+    sc = float(g["p"]["j0z"][sv[0] - 1] / rD[0])
+    po = oracle.Params(g["p"])
+    args = (tD, sv, rD, g["zD"], g["lay"])
+    so, do, sps, spd = oracle_with_noise(po, args, ts_scale=sc, carry=True, nsamples=2)
+    _, _, fo = oracle.eval_grid(po, *args, ts_scale=sc, carry=True)
+    sg, dg, fg = ub.eval_grid(g["prm"], *args, ts_scale=sc, want_flags=True)
+    assert np.array_equal(fo, fg)      # (no point of this grid is stale: the carry is exercised on
+    check_parity(sg, dg, so, do, sps, spd, what="C5a carry")   # the 128-z kernel in test_gpu_parity.py)
+
+
+def test_grid8_equals_lanes_z_kernel(c5a):
+    """The persistent 128-z kernel and the 64-z lanes<->z kernel implement the same arithmetic
+    except for the z-recurrence of the exponentials: results agree far below the parity bar."""
+    g = c5a
+    ub.force_kernel("grid2")
     try:
         s2, d2, f2 = ub.eval_grid(g["prm"], g["tD"][2:4], g["sv"][2:4], g["rD"][::16], g["zD"], g["lay"], want_flags=True)
     finally:
-        os.environ.pop("UNC_FORCE_KERNEL", None)
+        ub.force_kernel(None)
     s4, f4 = g["s"][2:4][:, ::16], g["fl"][2:4][:, ::16]
     assert np.array_equal(f2, f4)
     ok = np.isfinite(s2) & np.isfinite(s4)
@@ -126,9 +142,9 @@ def test_grid4_equals_grid2_kernel_bitwise_semantics(c5a):
     assert np.median(rel) < 1e-12 and (rel < 1e-7).mean() > 0.98
 
 
-def test_grid8_equals_grid4_on_odd_column_counts_and_ragged_z(c5a):
-    """lh_grid8_kernel (8 z-slots per lane, two Laplace parameters per warp) against
-    lh_grid4_kernel on shapes that exercise its edges: odd numbers of columns, z-blocks that
+def test_grid8_on_odd_column_counts_and_ragged_z(c5a):
+    """lh_grid8_kernel (8 z-slots per lane, two Laplace parameters per warp) against the
+    lanes<->z kernel on shapes that exercise its edges: odd numbers of columns, z-blocks that
     are not full, a second partial z-block."""
     g = c5a
     for nr, nt, zsel in ((5, 1, slice(0, 128)), (3, 3, slice(0, 100)), (2, 1, slice(0, 128, 1))):
@@ -136,11 +152,11 @@ def test_grid8_equals_grid4_on_odd_column_counts_and_ragged_z(c5a):
         rD = g["rD"][100:100 + 37 * nr:37]
         zD, lay = g["zD"][zsel], g["lay"][zsel]
         s8, d8, f8 = ub.eval_grid(g["prm"], tD, sv, rD, zD, lay, want_flags=True)
-        os.environ["UNC_FORCE_KERNEL"] = "grid4"
+        ub.force_kernel("grid2")
         try:
             s4, d4, f4 = ub.eval_grid(g["prm"], tD, sv, rD, zD, lay, want_flags=True)
         finally:
-            os.environ.pop("UNC_FORCE_KERNEL", None)
+            ub.force_kernel(None)
         assert np.array_equal(f8, f4)
         assert np.array_equal(np.isnan(s8), np.isnan(s4))
         ok = np.isfinite(s4)
@@ -151,11 +167,30 @@ def test_grid8_equals_grid4_on_odd_column_counts_and_ragged_z(c5a):
     lay = ub.zlay(z, g["p"]["lD"], g["p"]["dD"])
     tD, sv, rD = g["tD"][4:5], g["sv"][4:5], g["rD"][300:303]
     s8, d8 = ub.eval_grid(g["prm"], tD, sv, rD, z, lay)
-    os.environ["UNC_FORCE_KERNEL"] = "point"
+    ub.force_kernel("point")
     try:
         sp_, dp_ = ub.eval_grid(g["prm"], tD, sv, rD, z, lay)
     finally:
-        os.environ.pop("UNC_FORCE_KERNEL", None)
+        ub.force_kernel(None)
     ok = np.isfinite(sp_)
     rel = np.abs(s8[ok] - sp_[ok]) / np.maximum(np.abs(sp_[ok]), 1e-300)
     assert np.median(rel) < 1e-12 and (rel < 1e-6).mean() > 0.98
+
+
+def test_single_process_multi_gpu_sharding_is_bitwise_invariant(c5a):
+    """unc_eval_grid_ex(ngpu = all) on one grid, columns split across the visible GPUs (shard
+    boundaries fall inside time rows when nt is not a multiple of ngpu), with and without the
+    carry: bitwise the single-GPU result.  With one visible GPU this degenerates to ngpu=1."""
+    g = c5a
+    n = ub.device_count()
+    tD, sv, rD = g["tD"][1:4], g["sv"][1:4], g["rD"][:90]
+    s1, d1, f1 = ub.eval_grid(g["prm"], tD, sv, rD, g["zD"], g["lay"], ngpu=1, want_flags=True)
+    assert np.array_equal(s1, g["s"][1:4][:, :90], equal_nan=True)
+    for k in sorted({n, max(1, n - 1)}):
+        sk, dk, fk = ub.eval_grid(g["prm"], tD, sv, rD, g["zD"], g["lay"], ngpu=k, want_flags=True)
+        assert np.array_equal(sk, s1, equal_nan=True) and np.array_equal(dk, d1, equal_nan=True)
+        assert np.array_equal(fk, f1)
+    sc = float(g["p"]["j0z"][sv[0] - 1] / rD[40])
+    a1 = ub.eval_grid(g["prm"], tD, sv, rD, g["zD"], g["lay"], ts_scale=sc, ngpu=1)
+    an = ub.eval_grid(g["prm"], tD, sv, rD, g["zD"], g["lay"], ts_scale=sc, ngpu=0)
+    assert np.array_equal(a1[0], an[0], equal_nan=True) and np.array_equal(a1[1], an[1], equal_nan=True)

@@ -222,3 +222,16 @@ def kernel_launch_count():
 
 def shutdown():
     _ck(lib().unc_shutdown())
+
+
+def set_carry(on):
+    """unc_set_carry: reference-compatible grid calls inherit stale infint (default on)."""
+    _ck(lib().unc_set_carry(1 if on else 0))
+
+
+_KERNELS = {None: 0, "auto": 0, "point": 1, "grid": 2, "grid2": 3}
+
+
+def force_kernel(which=None):
+    """Test hook (unc_debug_force_kernel): None/'auto', 'point', 'grid', 'grid2'."""
+    _ck(lib().unc_debug_force_kernel(_KERNELS[which]))

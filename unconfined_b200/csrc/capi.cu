@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -19,6 +20,7 @@
 
 #include "../../include/unconfined_b200.h"
 #include "kernels.cuh"
+#include "carry.cuh"
 
 namespace {
 
@@ -128,7 +130,7 @@ void gauss_lobatto(int ord, std::vector<double> &gx, std::vector<double> &gw) {
 struct HostPlan {
   unc::DevParams P;
   std::vector<double> blob;  // ts_T | ts_wc | gl_x | gl_w | j0z | time_par | moench_gamma
-  size_t off_T, off_wc, off_glx, off_glw, off_j0z, off_tp, off_mg;
+  size_t off_T, off_wc, off_glx, off_glw, off_j0z, off_tp, off_mg, off_lw;
 };
 
 int make_plan(const unc_params *prm, HostPlan &hp) {
@@ -240,6 +242,12 @@ int make_plan(const unc_params *prm, HostPlan &hp) {
   hp.off_tp = push(prm->time_par, prm->n_time_par);
   double zero = 0.0;
   hp.off_mg = P.moench_M ? push(prm->moench_gamma, P.moench_M) : push(&zero, 1);
+  {
+    std::vector<double> all;   // the levels' own weights (error-budget builds, UNC_BUDGET_NEVILLE)
+    for (int m = 0; m < P.R; ++m) all.insert(all.end(), lw[m].begin(), lw[m].end());
+    hp.off_lw = push(all.data(), all.size());
+    P.ts_k = prm->ts_k;
+  }
   return UNC_OK;
 }
 
@@ -259,15 +267,40 @@ struct DevBuf {
   void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
 };
 
+// Everything a launch writes lives in the resources of the stream it is enqueued on: the
+// persistent grid kernel's totlap scratch and work counter, the uploaded tables and the
+// carry post-pass buffers.  Two calls on different streams therefore never share mutable
+// device state; calls on one stream are ordered by the stream.
+struct StreamRes {
+  DevBuf tables, scratch, counter;
+  std::vector<double> blob_cached;
+  // carry post-pass
+  DevBuf mask, slot, need, src_slot, list, src_list, fix_src, fix_val, fix_out, counts, cin;
+  void release() {
+    for (DevBuf *b : {&tables, &scratch, &counter, &mask, &slot, &need, &src_slot, &list, &src_list,
+                      &fix_src, &fix_val, &fix_out, &counts, &cin})
+      b->release();
+  }
+};
+
 struct DevCtx {
   bool init = false;
   cudaStream_t stream = nullptr;
-  DevBuf tables, in, out, scratch, counter;
+  DevBuf in, out;
   int sm_count = 0;
-  std::vector<double> blob_cached;
   bool smem_set[32] = {false};
+  std::map<cudaStream_t, StreamRes> res;
 };
 DevCtx g_ctx[16];
+std::atomic<int> g_carry{1};   // unc_set_carry
+std::atomic<int> g_force{0};   // unc_debug_force_kernel: 0 auto, 1 point, 2 grid, 3 grid (lanes<->z kernel only)
+
+// the library switches devices internally; the caller's current device is restored on return
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 int ensure_ctx(int dev) {
   if (dev < 0 || dev >= 16) return fail(UNC_ERR_BAD_ARG, "device %d out of range", dev);
@@ -281,18 +314,18 @@ int ensure_ctx(int dev) {
   return UNC_OK;
 }
 
-int upload_tables(int dev, HostPlan &hp, cudaStream_t st) {
-  DevCtx &c = g_ctx[dev];
+int upload_tables(StreamRes &r, HostPlan &hp, cudaStream_t st) {
   size_t bytes = hp.blob.size() * sizeof(double);
-  int rc = c.tables.ensure(bytes);
+  if (bytes > r.tables.cap) r.blob_cached.clear();
+  int rc = r.tables.ensure(bytes);
   if (rc) return rc;
-  if (c.blob_cached != hp.blob) {
+  if (r.blob_cached != hp.blob) {
     // tables are a few KB: synchronous semantics are fine, but stay on the job's stream
-    CK(cudaMemcpyAsync(c.tables.ptr, hp.blob.data(), bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(r.tables.ptr, hp.blob.data(), bytes, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
-    c.blob_cached = hp.blob;
+    r.blob_cached = hp.blob;
   }
-  const double *b = (const double *)c.tables.ptr;
+  const double *b = (const double *)r.tables.ptr;
   hp.P.ts_T = b + hp.off_T;
   hp.P.ts_wc = b + hp.off_wc;
   hp.P.gl_x = b + hp.off_glx;
@@ -300,11 +333,12 @@ int upload_tables(int dev, HostPlan &hp, cudaStream_t st) {
   hp.P.j0z = b + hp.off_j0z;
   hp.P.time_par = b + hp.off_tp;
   hp.P.moench_gamma = b + hp.off_mg;
+  hp.P.ts_lw = b + hp.off_lw;
   return UNC_OK;
 }
 
 template <int ZT>
-int launch_zt(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
+int launch_zt(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st, long long nblk_fix = -1) {
   const int na = P.nts_pad + P.gl_rounds * 32;
   const size_t smem = unc::smem_bytes(P.np, P.nacc, na, ZT);
   if (smem > 227 * 1024) return fail(UNC_ERR_UNSUPPORTED, "shared memory need %zu B exceeds 227 KB", smem);
@@ -315,7 +349,7 @@ int launch_zt(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t 
     c.smem_set[ZT] = true;
   }
   const long long ntiles = (J.nz + ZT - 1) / ZT;
-  const long long nblk = J.ncol * ntiles;
+  const long long nblk = nblk_fix >= 0 ? nblk_fix : J.ncol * ntiles;
   if (nblk <= 0) return UNC_OK;
   if (nblk > 2147483647LL) return fail(UNC_ERR_UNSUPPORTED, "too many work items (%lld)", nblk);
   unc::lh_point_kernel<ZT><<<(unsigned)nblk, UNC_THREADS, smem, st>>>(P, J);
@@ -343,41 +377,11 @@ int launch_grid_zl(int dev, const unc::DevParams &P, const unc::Job &J, cudaStre
   return UNC_OK;
 }
 
-// 128 z per work item, persistent CTAs drawing items from an atomic counter; totlap in a
-// per-CTA global scratch slot (kernels.cuh: lh_grid4_kernel)
+// 128 z per work item, persistent CTAs drawing items from an atomic counter, eight z-slots per
+// lane and two Laplace parameters per warp; totlap in a per-CTA global scratch slot
+// (kernels.cuh: lh_grid8_kernel).  Scratch and counter belong to the launch stream.
 template <int NW>
-int launch_grid4_nw(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
-  const int NA = P.N + P.nacc * P.G;
-  const size_t smem = unc::grid4_smem_bytes(P.np, (NA + 31) & ~31, NW);
-  if (smem > 227 * 1024) return fail(UNC_ERR_UNSUPPORTED, "shared memory need %zu B exceeds 227 KB", smem);
-  DevCtx &c = g_ctx[dev];
-  if (!c.smem_set[NW % 9]) {
-    CK(cudaFuncSetAttribute(unc::lh_grid4_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    c.smem_set[NW % 9] = true;
-  }
-  const long long nitems = J.ncol * ((J.nz + 127) / 128);
-  if (nitems <= 0) return UNC_OK;
-  if (nitems > 4000000000LL) return fail(UNC_ERR_UNSUPPORTED, "too many work items (%lld)", nitems);
-  int occ = 2;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, unc::lh_grid4_kernel<NW>, NW * 32, smem));
-  if (occ < 1) occ = 1;
-  const int grid = (int)std::min<long long>(nitems, (long long)c.sm_count * occ);
-  int rc = c.scratch.ensure((size_t)grid * 2 * P.np * 128 * sizeof(unc::cplx));   // two totlap slots per CTA
-  if (rc) return rc;
-  const bool fresh_counter = c.counter.ptr == nullptr;
-  rc = c.counter.ensure(256);
-  if (rc) return rc;
-  if (fresh_counter) CK(cudaMemsetAsync(c.counter.ptr, 0, 256, st));   // the kernel re-arms it itself
-  unc::lh_grid4_kernel<NW><<<grid, NW * 32, smem, st>>>(P, J, (unc::cplx *)c.scratch.ptr,
-                                                         (unsigned int *)c.counter.ptr);
-  g_launches++;
-  CK(cudaGetLastError());
-  return UNC_OK;
-}
-
-// second generation: eight z-slots per lane, two Laplace parameters per warp (lh_grid8_kernel)
-template <int NW>
-int launch_grid8_nw(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
+int launch_grid8_nw(int dev, StreamRes &r, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
   const int NA = P.N + P.nacc * P.G;
   const size_t smem = unc::grid8_smem_bytes(P.np, (NA + 31) & ~31, NW);
   if (smem > 227 * 1024) return fail(UNC_ERR_UNSUPPORTED, "shared memory need %zu B exceeds 227 KB", smem);
@@ -396,57 +400,124 @@ int launch_grid8_nw(int dev, const unc::DevParams &P, const unc::Job &J, cudaStr
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, unc::lh_grid8_kernel<NW>, NW * 32, smem));
   if (occ < 1) occ = 1;
   const int grid = (int)std::min<long long>(nitems, (long long)c.sm_count * occ);
-  int rc = c.scratch.ensure((size_t)grid * 2 * P.np * 128 * sizeof(unc::cplx));   // two totlap slots per CTA
+  int rc = r.scratch.ensure((size_t)grid * 2 * P.np * 128 * sizeof(unc::cplx));   // two totlap slots per CTA
   if (rc) return rc;
-  const bool fresh_counter = c.counter.ptr == nullptr;
-  rc = c.counter.ensure(256);
+  rc = r.counter.ensure(256);
   if (rc) return rc;
-  if (fresh_counter) CK(cudaMemsetAsync(c.counter.ptr, 0, 256, st));   // the kernel re-arms it itself
-  unc::lh_grid8_kernel<NW><<<grid, NW * 32, smem, st>>>(P, J, (unc::cplx *)c.scratch.ptr,
-                                                         (unsigned int *)c.counter.ptr);
+  // armed on the launch stream before every launch (the kernel also re-arms it when it ends, so
+  // that a profiler's replays of the launch start from zero as well)
+  CK(cudaMemsetAsync(r.counter.ptr, 0, 256, st));
+  unc::lh_grid8_kernel<NW><<<grid, NW * 32, smem, st>>>(P, J, (unc::cplx *)r.scratch.ptr,
+                                                         (unsigned int *)r.counter.ptr);
   g_launches++;
   CK(cudaGetLastError());
   return UNC_OK;
 }
 
-int launch_grid4(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
-#ifdef UNC_GRID4_NW
-  return launch_grid4_nw<UNC_GRID4_NW>(dev, P, J, st);   // experiments (tools/run_variants.sh)
-#else
-  return launch_grid4_nw<8>(dev, P, J, st);
-#endif
-}
-
-int launch_grid(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
-  const char *force = getenv("UNC_FORCE_KERNEL");
-  const bool no4 = force && !strcmp(force, "grid2");
-  const bool only4 = force && !strcmp(force, "grid4");
+int launch_grid(int dev, StreamRes &r, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
+  const bool small_only = g_force.load() == 3;
 #ifdef UNC_GRID8_NW
-  if (J.nz >= 96 && !no4 && !only4) return launch_grid8_nw<UNC_GRID8_NW>(dev, P, J, st);   // experiments
+  if (J.nz >= 96 && !small_only) return launch_grid8_nw<UNC_GRID8_NW>(dev, r, P, J, st);   // experiments
 #else
-  if (J.nz >= 96 && !no4 && !only4) return launch_grid8_nw<8>(dev, P, J, st);
+  if (J.nz >= 96 && !small_only) return launch_grid8_nw<8>(dev, r, P, J, st);
 #endif
-  if (J.nz >= 96 && !no4) return launch_grid4(dev, P, J, st);
   // two z per lane (64 z per CTA) halves the per-(a,p) work per point; keep one z per lane
   // for short columns and when the larger totlap tile would not fit twice per SM
   if (J.nz > 32 && P.np <= 53) return launch_grid_zl<2>(dev, P, J, st);
   return launch_grid_zl<1>(dev, P, J, st);
 }
 
-// kernel selection: lanes<->z (grid kernel) once a column has enough z to fill most of a
-// warp; otherwise lanes<->abscissae (point kernel).  UNC_FORCE_KERNEL=point|grid overrides.
-int launch(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
-  const char *force = getenv("UNC_FORCE_KERNEL");
+// kernel selection: lanes<->z (grid kernels) once a column has enough z to fill most of a
+// warp; otherwise lanes<->abscissae (point kernel).  unc_debug_force_kernel overrides (tests).
+int launch(int dev, StreamRes &r, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
+  const int force = g_force.load();
   bool grid = J.nz >= 12;
   // a small contour grid (fewer column CTAs than SMs) is a latency problem: the point kernel
   // spreads it over nz/4 times as many CTAs (hantush-contours deck, 30 r x 20 z: 6.9 ms -> <1 ms)
   if (grid && J.nz < 96 && J.ncol * ((J.nz + 31) / 32) < (long long)g_ctx[dev].sm_count) grid = false;
-  if (force && !strcmp(force, "point")) grid = false;
-  if (force && (!strcmp(force, "grid") || !strcmp(force, "grid2") || !strcmp(force, "grid4"))) grid = true;
-  if (grid) return launch_grid(dev, P, J, st);
+  if (force == 1) grid = false;
+  if (force == 2 || force == 3) grid = true;
+  if (grid) return launch_grid(dev, r, P, J, st);
   if (J.nz >= 4) return launch_zt<4>(dev, P, J, st);
   if (J.nz >= 2) return launch_zt<2>(dev, P, J, st);
   return launch_zt<1>(dev, P, J, st);
+}
+
+// ---- stale-infint carry (driver.f90:205-214), see carry.cuh --------------------------------
+// d_mask: per point of the WHOLE job (global column order), bit p = infint(p,z) stale.
+// Jg: the global job (col0 = 0; device pointers of the inputs; s/ds = device outputs to patch
+// in place, or NULL).  On return *nf_out = number of re-inverted points; if h_list/h_s/h_ds are
+// given they receive the compact results (point index, s, ds).  Synchronises `st` twice.
+int carry_postpass(int dev, StreamRes &r, const unc::DevParams &P, unc::Job Jg, const unsigned long long *d_mask,
+                   cudaStream_t st, long long *nf_out, std::vector<int> *h_list, std::vector<double> *h_s,
+                   std::vector<double> *h_ds) {
+  const long long npts = Jg.ncol * (long long)Jg.nz;
+  *nf_out = 0;
+  if (npts <= 0) return UNC_OK;
+  if (npts > 2147483647LL) return fail(UNC_ERR_UNSUPPORTED, "carry post-pass: more than 2^31 points");
+  const int np = P.np, nz = Jg.nz;
+  int rc;
+  if ((rc = r.counts.ensure(64))) return rc;
+  if ((rc = r.slot.ensure((size_t)npts * sizeof(int)))) return rc;
+  if ((rc = r.list.ensure((size_t)npts * sizeof(int)))) return rc;
+  unsigned int *d_cnt = (unsigned int *)r.counts.ptr;
+  CK(cudaMemsetAsync(d_cnt, 0, 64, st));
+  const int TB = 256;
+  const unsigned nb = (unsigned)((npts + TB - 1) / TB);
+  unc::carry_list_kernel<<<nb, TB, 0, st>>>(d_mask, npts, (int *)r.list.ptr, (int *)r.slot.ptr, d_cnt);
+  g_launches++;
+  unsigned int h_cnt[2] = {0, 0};
+  CK(cudaMemcpyAsync(&h_cnt[0], d_cnt, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const long long nf = h_cnt[0];
+  if (nf == 0) return UNC_OK;
+  // sources
+  if ((rc = r.need.ensure((size_t)npts * sizeof(unsigned long long)))) return rc;
+  if ((rc = r.fix_src.ensure((size_t)nf * np * sizeof(int)))) return rc;
+  if ((rc = r.src_slot.ensure((size_t)npts * sizeof(int)))) return rc;
+  if ((rc = r.src_list.ensure((size_t)npts * sizeof(int)))) return rc;
+  CK(cudaMemsetAsync(r.need.ptr, 0, (size_t)npts * sizeof(unsigned long long), st));
+  unc::carry_scan_kernel<<<(unsigned)((nz * np + 127) / 128), 128, 0, st>>>(
+      d_mask, Jg.ncol, nz, np, (const int *)r.slot.ptr, (int *)r.fix_src.ptr, (unsigned long long *)r.need.ptr);
+  unc::carry_list_kernel<<<nb, TB, 0, st>>>((const unsigned long long *)r.need.ptr, npts, (int *)r.src_list.ptr,
+                                            (int *)r.src_slot.ptr, d_cnt + 1);
+  g_launches += 2;
+  CK(cudaMemcpyAsync(&h_cnt[1], d_cnt + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const long long ns = h_cnt[1];
+  if ((rc = r.fix_val.ensure((size_t)std::max<long long>(ns, 1) * np * 2 * sizeof(double)))) return rc;
+  if ((rc = r.fix_out.ensure((size_t)nf * 2 * sizeof(double)))) return rc;
+  unc::carry_link_kernel<<<(unsigned)((nf * np + TB - 1) / TB), TB, 0, st>>>(
+      (const int *)r.list.ptr, nf, nz, np, d_mask, (const int *)r.src_slot.ptr, (int *)r.fix_src.ptr);
+  g_launches++;
+  CK(cudaGetLastError());
+  // pass 1: Wynn results of the source points for the p somebody inherits
+  unc::Job Js = Jg;
+  Js.s = Js.ds = nullptr; Js.flags = nullptr; Js.smask = nullptr;
+  Js.fix_mode = 1;
+  Js.fix_list = (const int *)r.src_list.ptr;
+  Js.fix_need = (const unsigned long long *)r.need.ptr;
+  Js.fix_val = (double *)r.fix_val.ptr;
+  if (ns > 0 && (rc = launch_zt<1>(dev, P, Js, st, ns))) return rc;
+  // pass 2: the flagged points again, with the inherited values
+  unc::Job Jd = Jg;
+  Jd.flags = nullptr; Jd.smask = nullptr;
+  Jd.fix_mode = 2;
+  Jd.fix_list = (const int *)r.list.ptr;
+  Jd.fix_src = (const int *)r.fix_src.ptr;
+  Jd.fix_val = (double *)r.fix_val.ptr;
+  Jd.fix_s = (double *)r.fix_out.ptr;
+  Jd.fix_ds = Jd.fix_s + nf;
+  if ((rc = launch_zt<1>(dev, P, Jd, st, nf))) return rc;
+  if (h_list) {
+    h_list->resize(nf); h_s->resize(nf); h_ds->resize(nf);
+    CK(cudaMemcpyAsync(h_list->data(), r.list.ptr, nf * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_s->data(), Jd.fix_s, nf * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_ds->data(), Jd.fix_ds, nf * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  *nf_out = nf;
+  return UNC_OK;
 }
 
 int check_common(const double *tD, const int32_t *sv, const double *rD, const double *zD,
@@ -475,6 +546,7 @@ struct Shard {
   long long c0, c1;  // columns [c0,c1)
   int rc = 0;
   std::string err;
+  long long nflagged = 0;
 };
 
 struct HostJob {
@@ -484,7 +556,62 @@ struct HostJob {
   const double *tD; const int32_t *sv; const double *rD; const double *zD; const int32_t *zLay;
   const double *ts;
   double *s, *ds; int32_t *flags;
+  bool carry;                    // grid jobs with ts given: reproduce the reference's stale infint
+  unsigned long long *hmask;     // carry: host copy of the per-point stale masks (global order)
 };
+
+// device layout of the inputs of columns [c0,c1): grid jobs get the whole t/r/z axes (a few KB)
+// and address them by global column (Job::col0); point lists get their own slice
+struct DevInputs {
+  double *tD, *rD, *zD, *ts;
+  int32_t *sv, *lay;
+};
+
+int upload_inputs(DevBuf &buf, const HostJob &hj, long long c0, long long c1, cudaStream_t st, DevInputs &d) {
+  const long long nc = c1 - c0;
+  const size_t n_t = hj.grid ? (size_t)hj.nt : (size_t)nc;
+  const size_t n_r = hj.grid ? (size_t)hj.nr : (size_t)nc;
+  const size_t n_z = hj.grid ? (size_t)hj.nz : (size_t)nc;
+  const size_t n_ts = hj.ts ? (size_t)nc : 0;
+  const long long off = hj.grid ? 0 : c0;
+  int rc = buf.ensure((n_t + n_r + n_z + n_ts) * sizeof(double) + (n_t + n_z) * sizeof(int32_t) + 64);
+  if (rc) return rc;
+  d.tD = (double *)buf.ptr;
+  d.rD = d.tD + n_t;
+  d.zD = d.rD + n_r;
+  d.ts = d.zD + n_z;
+  d.sv = (int32_t *)(d.ts + n_ts);
+  d.lay = d.sv + n_t;
+  CK(cudaMemcpyAsync(d.tD, hj.tD + off, n_t * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d.sv, hj.sv + off, n_t * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d.rD, hj.rD + off, n_r * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d.zD, hj.zD + off, n_z * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d.lay, hj.zLay + off, n_z * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (hj.ts) CK(cudaMemcpyAsync(d.ts, hj.ts + c0, n_ts * sizeof(double), cudaMemcpyHostToDevice, st));
+  else d.ts = nullptr;
+  return UNC_OK;
+}
+
+unc::Job make_job(const HostJob &hj, const DevInputs &d, long long c0, long long nc) {
+  unc::Job J;
+  std::memset(&J, 0, sizeof J);
+  J.ncol = nc;
+  J.nz = hj.nz;
+  J.tD = d.tD; J.sv = d.sv; J.rD = d.rD; J.zD = d.zD; J.zLay = d.lay;
+  J.ts_scale = d.ts;
+  if (hj.grid) {
+    J.col0 = c0;          // global column c: t = c / nr, r = c % nr (driver.f90:100,113 loop order)
+    J.tdiv = hj.nr;
+    J.rmod = hj.nr;
+    J.zstride = 0;
+  } else {
+    J.col0 = 0;
+    J.tdiv = 1;
+    J.rmod = nc;
+    J.zstride = 1;
+  }
+  return J;
+}
 
 int run_shard(const unc_params *prm, const HostJob &hj, Shard &sh) {
   HostPlan hp;
@@ -494,100 +621,87 @@ int run_shard(const unc_params *prm, const HostJob &hj, Shard &sh) {
   if (rc) return rc;
   DevCtx &c = g_ctx[sh.dev];
   cudaStream_t st = c.stream;
-  rc = upload_tables(sh.dev, hp, st);
+  StreamRes &r = c.res[st];
+  rc = upload_tables(r, hp, st);
   if (rc) return rc;
   const long long nc = sh.c1 - sh.c0;
   if (nc <= 0) return UNC_OK;
   const int nz = hj.nz;
-  // input layout on device: tD | rD | zD | ts | sv | zLay
-  size_t n_t, n_r, n_z;
-  long long t_first = 0, t_last = 0;
-  if (hj.grid) {
-    t_first = sh.c0 / hj.nr;
-    t_last = (sh.c1 - 1) / hj.nr;
-    n_t = (size_t)(t_last - t_first + 1);
-    n_r = hj.nr;
-    n_z = nz;
-  } else {
-    n_t = n_r = n_z = (size_t)nc;
-  }
-  const size_t n_ts = hj.ts ? (size_t)nc : 0;
-  size_t bytes_in = (n_t + n_r + n_z + n_ts) * sizeof(double) + (n_t + n_z) * sizeof(int32_t) + 64;
-  rc = c.in.ensure(bytes_in);
+  const size_t npts = (size_t)nc * nz;
+  DevInputs di;
+  rc = upload_inputs(c.in, hj, sh.c0, sh.c1, st, di);
   if (rc) return rc;
-  rc = c.out.ensure((size_t)nc * nz * (2 * sizeof(double) + sizeof(int32_t)) + 64);
+  // outputs: s | ds | masks (carry) | flags | flagged-count
+  rc = c.out.ensure(npts * (2 * sizeof(double) + sizeof(unsigned long long) + sizeof(int32_t)) + 64);
   if (rc) return rc;
-  double *d_tD = (double *)c.in.ptr;
-  double *d_rD = d_tD + n_t;
-  double *d_zD = d_rD + n_r;
-  double *d_ts = d_zD + n_z;
-  int32_t *d_sv = (int32_t *)(d_ts + n_ts);
-  int32_t *d_lay = d_sv + n_t;
   double *d_s = (double *)c.out.ptr;
-  double *d_ds = d_s + (size_t)nc * nz;
-  int32_t *d_fl = (int32_t *)(d_ds + (size_t)nc * nz);
-  const long long toff = hj.grid ? t_first : sh.c0;
-  const long long roff = hj.grid ? 0 : sh.c0;
-  const long long zoff = hj.grid ? 0 : sh.c0;
-  CK(cudaMemcpyAsync(d_tD, hj.tD + toff, n_t * sizeof(double), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_sv, hj.sv + toff, n_t * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_rD, hj.rD + roff, n_r * sizeof(double), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_zD, hj.zD + zoff, n_z * sizeof(double), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_lay, hj.zLay + zoff, n_z * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  if (hj.ts) CK(cudaMemcpyAsync(d_ts, hj.ts + sh.c0, n_ts * sizeof(double), cudaMemcpyHostToDevice, st));
-  unc::Job J;
-  J.ncol = nc;
-  J.nz = nz;
-  J.tD = d_tD; J.sv = d_sv; J.rD = d_rD; J.zD = d_zD; J.zLay = d_lay;
-  J.ts_scale = hj.ts ? d_ts : nullptr;
-  J.s = d_s; J.ds = d_ds; J.flags = hj.flags ? d_fl : nullptr;
-  if (hj.grid) {
-    // local column lc = c - c0; global c = lc + c0: t = c / nr, r = c % nr.  Shift so the
-    // kernel's (lc / tdiv, lc % rmod) addressing works: pad by starting at column
-    // c0 - t_first*nr inside the first time row.
-    J.tdiv = hj.nr;
-    J.rmod = hj.nr;
-    J.zstride = 0;
-  } else {
-    J.tdiv = 1;
-    J.rmod = nc;
-    J.zstride = 1;
+  double *d_ds = d_s + npts;
+  unsigned long long *d_mask = (unsigned long long *)(d_ds + npts);
+  int32_t *d_fl = (int32_t *)(d_mask + npts);
+  unsigned int *d_cnt = (unsigned int *)(d_fl + npts);
+  unc::Job J = make_job(hj, di, sh.c0, nc);
+  J.s = d_s; J.ds = d_ds;
+  J.flags = hj.flags ? d_fl : nullptr;
+  J.smask = hj.carry ? d_mask : nullptr;
+  rc = launch(sh.dev, r, hp.P, J, st);
+  if (rc) return rc;
+  unsigned int h_cnt = 0;
+  if (hj.carry) {
+    CK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned int), st));
+    unc::carry_list_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(d_mask, (long long)npts, nullptr,
+                                                                            nullptr, d_cnt);
+    g_launches++;
+    CK(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
   }
-  if (hj.grid && (sh.c0 % hj.nr) != 0) {
-    // shards are cut on time-row boundaries by the caller whenever possible; otherwise
-    // run the partial rows one by one
-    long long c = sh.c0;
-    while (c < sh.c1) {
-      long long row_end = std::min(sh.c1, (c / hj.nr + 1) * hj.nr);
-      unc::Job Jr = J;
-      Jr.ncol = row_end - c;
-      Jr.tdiv = 1LL << 40;  // single time row
-      Jr.tD = d_tD + (c / hj.nr - t_first);
-      Jr.sv = d_sv + (c / hj.nr - t_first);
-      Jr.rD = d_rD + (c % hj.nr);
-      Jr.rmod = 1LL << 40;
-      Jr.ts_scale = hj.ts ? d_ts + (c - sh.c0) : nullptr;
-      Jr.s = d_s + (c - sh.c0) * nz;
-      Jr.ds = d_ds + (c - sh.c0) * nz;
-      Jr.flags = hj.flags ? d_fl + (c - sh.c0) * nz : nullptr;
-      rc = launch(sh.dev, hp.P, Jr, st);
-      if (rc) return rc;
-      c = row_end;
-    }
-  } else {
-    rc = launch(sh.dev, hp.P, J, st);
-    if (rc) return rc;
-  }
-  CK(cudaMemcpyAsync(hj.s + sh.c0 * nz, d_s, (size_t)nc * nz * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(hj.ds + sh.c0 * nz, d_ds, (size_t)nc * nz * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hj.s + sh.c0 * nz, d_s, npts * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hj.ds + sh.c0 * nz, d_ds, npts * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (hj.flags)
-    CK(cudaMemcpyAsync(hj.flags + sh.c0 * nz, d_fl, (size_t)nc * nz * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hj.flags + sh.c0 * nz, d_fl, npts * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  sh.nflagged = h_cnt;
+  if (hj.carry && h_cnt > 0) {
+    CK(cudaMemcpyAsync(hj.hmask + sh.c0 * nz, d_mask, npts * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
   return UNC_OK;
 }
 
-int run_host(const unc_params *prm, const HostJob &hj, int ngpu) {
+// carry post-pass for host-array jobs: after every shard has finished, on one device, over the
+// whole job in the reference's column order (the chain crosses shard boundaries)
+int carry_host(const unc_params *prm, const HostJob &hj, int dev) {
+  HostPlan hp;
+  int rc = make_plan(prm, hp);
+  if (rc) return rc;
+  rc = ensure_ctx(dev);
+  if (rc) return rc;
+  DevCtx &c = g_ctx[dev];
+  cudaStream_t st = c.stream;
+  StreamRes &r = c.res[st];
+  rc = upload_tables(r, hp, st);
+  if (rc) return rc;
+  DevInputs di;
+  rc = upload_inputs(r.cin, hj, 0, hj.ncol, st, di);
+  if (rc) return rc;
+  const size_t npts = (size_t)hj.ncol * hj.nz;
+  rc = r.mask.ensure(npts * sizeof(unsigned long long));
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(r.mask.ptr, hj.hmask, npts * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+  unc::Job J = make_job(hj, di, 0, hj.ncol);
+  std::vector<int> list;
+  std::vector<double> vs, vds;
+  long long nf = 0;
+  rc = carry_postpass(dev, r, hp.P, J, (const unsigned long long *)r.mask.ptr, st, &nf, &list, &vs, &vds);
+  if (rc) return rc;
+  for (long long i = 0; i < nf; ++i) {
+    hj.s[list[i]] = vs[i];
+    hj.ds[list[i]] = vds[i];
+  }
+  return UNC_OK;
+}
+
+int run_host(const unc_params *prm, HostJob hj, int ngpu) {
   std::lock_guard<std::mutex> lk(g_mutex);
+  DeviceGuard guard;
   {
     HostPlan probe;   // parameter validation is host-only and comes before any device work
     int rc = make_plan(prm, probe);
@@ -598,31 +712,40 @@ int run_host(const unc_params *prm, const HostJob &hj, int ngpu) {
   if (avail <= 0) return fail(UNC_ERR_NO_DEVICE, "no CUDA device available (there is no CPU fallback)");
   int use = ngpu == 0 ? avail : std::min(ngpu, avail);
   if (hj.ncol < use) use = (int)std::max<long long>(1, hj.ncol);
-  if (use == 1) {
-    Shard sh{g_device, 0, hj.ncol};
-    return run_shard(prm, hj, sh);
+  std::vector<unsigned long long> hmask;
+  if (hj.carry) {
+    hmask.assign((size_t)hj.ncol * hj.nz, 0ull);
+    hj.hmask = hmask.data();
   }
-  // contiguous equal split of the columns; grid shards cut on time rows
-  // when there are enough rows, otherwise anywhere
+  // contiguous equal split of the columns over the devices g_device, g_device+1, ...
   std::vector<Shard> shards(use);
   for (int g = 0; g < use; ++g) {
-    long long c0 = hj.ncol * g / use, c1 = hj.ncol * (g + 1) / use;
-    shards[g].dev = g;
-    shards[g].c0 = c0;
-    shards[g].c1 = c1;
+    shards[g].dev = (g_device + g) % avail;
+    shards[g].c0 = hj.ncol * g / use;
+    shards[g].c1 = hj.ncol * (g + 1) / use;
   }
-  std::vector<std::thread> th;
-  for (int g = 0; g < use; ++g)
-    th.emplace_back([&, g]() {
-      shards[g].rc = run_shard(prm, hj, shards[g]);
-      if (shards[g].rc) shards[g].err = g_err;
-    });
-  for (auto &t : th) t.join();
-  for (int g = 0; g < use; ++g)
-    if (shards[g].rc) {
-      g_err = shards[g].err;
-      return shards[g].rc;
-    }
+  if (use == 1) {
+    shards[0].rc = run_shard(prm, hj, shards[0]);
+    if (shards[0].rc) return shards[0].rc;
+  } else {
+    std::vector<std::thread> th;
+    for (int g = 0; g < use; ++g)
+      th.emplace_back([&, g]() {
+        shards[g].rc = run_shard(prm, hj, shards[g]);
+        if (shards[g].rc) shards[g].err = g_err;
+      });
+    for (auto &t : th) t.join();
+    for (int g = 0; g < use; ++g)
+      if (shards[g].rc) {
+        g_err = shards[g].err;
+        return shards[g].rc;
+      }
+  }
+  if (hj.carry) {
+    long long nfl = 0;
+    for (auto &sh : shards) nfl += sh.nflagged;
+    if (nfl > 0) return carry_host(prm, hj, shards[0].dev);
+  }
   return UNC_OK;
 }
 
@@ -680,6 +803,7 @@ int unc_kernel_launch_count(int64_t *n) {
 int unc_measure_fp64_peak(double *flops) {
   if (!flops) return fail(UNC_ERR_BAD_ARG, "NULL");
   std::lock_guard<std::mutex> lk(g_mutex);
+  DeviceGuard guard;
   if (device_count() <= 0) return fail(UNC_ERR_NO_DEVICE, "no CUDA device available");
   int rc = ensure_ctx(g_device);
   if (rc) return rc;
@@ -714,14 +838,33 @@ int unc_measure_fp64_peak(double *flops) {
 
 int unc_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mutex);
+  DeviceGuard guard;
   for (int d = 0; d < 16; ++d) {
     DevCtx &c = g_ctx[d];
     if (!c.init) continue;
     cudaSetDevice(d);
-    c.tables.release(); c.in.release(); c.out.release(); c.scratch.release(); c.counter.release();
+    cudaDeviceSynchronize();
+    c.in.release(); c.out.release();
+    for (auto &kv : c.res) kv.second.release();
     cudaStreamDestroy(c.stream);
     c = DevCtx();
   }
+  return UNC_OK;
+}
+
+/* 1 (default): grid calls that pass ts_abscissa_scale (reference-compatible mode) also
+ * reproduce the reference's stale infint (driver.f90:205-214); 0: such points get infint = 0
+ * and UNC_FLAG_STALE_INFINT only, as calls with ts_abscissa_scale = NULL always do */
+int unc_set_carry(int32_t on) {
+  g_carry.store(on ? 1 : 0);
+  return UNC_OK;
+}
+
+/* test hook: pin the kernel family (0 auto, 1 point kernel, 2 grid kernels, 3 the lanes<->z
+ * grid kernel even for nz >= 96); never needed by a caller of the product */
+int unc_debug_force_kernel(int32_t which) {
+  if (which < 0 || which > 3) return fail(UNC_ERR_BAD_ARG, "which must be 0..3");
+  g_force.store(which);
   return UNC_OK;
 }
 
@@ -736,8 +879,9 @@ int unc_eval_grid_ex(const unc_params *prm, int32_t nt, const double *tD, const 
   if (!prm) return fail(UNC_ERR_BAD_ARG, "prm is NULL");
   rc = validate_sv(prm, nt, sv);
   if (rc) return rc;
+  // reference-compatible callers (ts_abscissa_scale given) also get the reference's stale infint
   HostJob hj{true, (long long)nt * nr, nt, nr, nz, tD, sv, rD, zD, zLay, ts_abscissa_scale,
-             totint, totintd, flags};
+             totint, totintd, flags, ts_abscissa_scale != nullptr && g_carry.load() != 0, nullptr};
   return run_host(prm, hj, ngpu);
 }
 
@@ -760,7 +904,8 @@ int unc_eval_points_ex(const unc_params *prm, int64_t n, const double *tD, const
   if (!prm) return fail(UNC_ERR_BAD_ARG, "prm is NULL");
   rc = validate_sv(prm, n, sv);
   if (rc) return rc;
-  HostJob hj{false, (long long)n, 0, 0, 1, tD, sv, rD, zD, zLay, ts_abscissa_scale, s, ds, flags};
+  // independent points: there is no "previous (t,r)" to inherit from
+  HostJob hj{false, (long long)n, 0, 0, 1, tD, sv, rD, zD, zLay, ts_abscissa_scale, s, ds, flags, false, nullptr};
   return run_host(prm, hj, ngpu);
 }
 
@@ -780,6 +925,7 @@ int unc_eval_grid_device(const unc_params *prm, int32_t nt, const double *d_tD,
   int rc = check_common(d_tD, d_sv, d_rD, d_zD, d_zLay, d_totint, d_totintd);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(g_mutex);
+  DeviceGuard guard;
   if (device_count() <= 0) return fail(UNC_ERR_NO_DEVICE, "no CUDA device available");
   HostPlan hp;
   rc = make_plan(prm, hp);
@@ -787,16 +933,29 @@ int unc_eval_grid_device(const unc_params *prm, int32_t nt, const double *d_tD,
   rc = ensure_ctx(g_device);
   if (rc) return rc;
   cudaStream_t st = stream ? (cudaStream_t)stream : (cudaStream_t)0;
-  rc = upload_tables(g_device, hp, st);
+  StreamRes &r = g_ctx[g_device].res[st];
+  rc = upload_tables(r, hp, st);
   if (rc) return rc;
   unc::Job J;
+  std::memset(&J, 0, sizeof J);
   J.ncol = (long long)nt * nr;
   J.nz = nz;
   J.tdiv = nr; J.rmod = nr; J.zstride = 0;
   J.tD = d_tD; J.sv = d_sv; J.rD = d_rD; J.zD = d_zD; J.zLay = d_zLay;
   J.ts_scale = d_ts_abscissa_scale;
   J.s = d_totint; J.ds = d_totintd; J.flags = d_flags;
-  return launch(g_device, hp.P, J, st);
+  const bool carry = d_ts_abscissa_scale != nullptr && g_carry.load() != 0;
+  if (carry) {
+    rc = r.mask.ensure((size_t)J.ncol * nz * sizeof(unsigned long long));
+    if (rc) return rc;
+    J.smask = (unsigned long long *)r.mask.ptr;
+  }
+  rc = launch(g_device, r, hp.P, J, st);
+  if (rc || !carry) return rc;
+  // reference-compatible mode: patch the stale points in place (synchronises the stream)
+  J.smask = nullptr;
+  long long nf = 0;
+  return carry_postpass(g_device, r, hp.P, J, (const unsigned long long *)r.mask.ptr, st, &nf, nullptr, nullptr, nullptr);
 }
 
 int unc_eval_points_device(const unc_params *prm, int64_t n, const double *d_tD,
@@ -808,6 +967,7 @@ int unc_eval_points_device(const unc_params *prm, int64_t n, const double *d_tD,
   int rc = check_common(d_tD, d_sv, d_rD, d_zD, d_zLay, d_s, d_ds);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(g_mutex);
+  DeviceGuard guard;
   if (device_count() <= 0) return fail(UNC_ERR_NO_DEVICE, "no CUDA device available");
   HostPlan hp;
   rc = make_plan(prm, hp);
@@ -815,16 +975,18 @@ int unc_eval_points_device(const unc_params *prm, int64_t n, const double *d_tD,
   rc = ensure_ctx(g_device);
   if (rc) return rc;
   cudaStream_t st = stream ? (cudaStream_t)stream : (cudaStream_t)0;
-  rc = upload_tables(g_device, hp, st);
+  StreamRes &r = g_ctx[g_device].res[st];
+  rc = upload_tables(r, hp, st);
   if (rc) return rc;
   unc::Job J;
+  std::memset(&J, 0, sizeof J);
   J.ncol = n;
   J.nz = 1;
   J.tdiv = 1; J.rmod = n; J.zstride = 1;
   J.tD = d_tD; J.sv = d_sv; J.rD = d_rD; J.zD = d_zD; J.zLay = d_zLay;
   J.ts_scale = d_ts_abscissa_scale;
   J.s = d_s; J.ds = d_ds; J.flags = d_flags;
-  return launch(g_device, hp.P, J, st);
+  return launch(g_device, r, hp.P, J, st);
 }
 
 // driver_io.f90:628-647

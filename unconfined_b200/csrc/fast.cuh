@@ -34,7 +34,17 @@ namespace unc {
 // m: sinh(eta) -> 1; udp(zD=1) of models 3/5 and the layer-3 branch form
 // sinh(eta dD)*cosh(eta z) -> up to 1+dD (laplace_hankel_solutions.f90:179,81); layer-2
 // products stay below 1; |z| itself for callers outside 0<=zD<=1.
+// Error-budget switches (tools/error_budget.py builds one library per switch and tabulates
+// |gpu - oracle| on the BASELINE decks; never defined in the product build):
+//   UNC_BUDGET_LITERAL   no closed forms: every abscissa takes the literal path
+//   UNC_BUDGET_LIBM      CUDA libm exp/sincos instead of exp_pm / sincos_q
+//   UNC_BUDGET_IEEE_DIV  IEEE division instead of rcp.approx + 2 Newton steps
+//   UNC_BUDGET_SEQSUM    point kernel: abscissae summed sequentially in the reference's order
+//   UNC_BUDGET_NEVILLE   point kernel: R level sums + extraptozero on the device (implies SEQSUM)
 __host__ __device__ __forceinline__ double fast_eta_max(const DevParams &P, int lay_mask, double zabs_max) {
+#ifdef UNC_BUDGET_LITERAL
+  return -1.0;
+#endif
   double m = 1.0;
   if (P.model == 3 || P.model == 5 || (lay_mask & 4)) m = 1.0 + P.dD;
   if (P.model == 6) m = 1.03;   // Delta0 = eta sinh(eta) - u cosh(eta): headroom for the factors eta, u
@@ -108,6 +118,10 @@ static inline double unc_hilo2d_h(int h, int l) {
 // need cosh x / sinh x without cancellation.
 __host__ __device__ __forceinline__ void exp_pm_core(double x, double *ep, double *em, double *c_out,
                                             double *s_out, int *k_out) {
+#ifdef UNC_BUDGET_LIBM
+  *ep = exp(x); *em = exp(-x); *c_out = cosh(x); *s_out = sinh(x); *k_out = 0;
+  return;
+#endif
   const double km = fma(x, KEXP[0], KEXP[3]);
   const int k = UNC_LOINT(km);
   const double kf = km - KEXP[3];
@@ -153,6 +167,10 @@ __host__ __device__ __forceinline__ rexp exp_pm(double x) {
 // two-term Cody-Waite reduction by pi/2 (the FMA keeps k*pi/2_hi exact), kernel
 // polynomials, quadrant fix-up on the sign/high words.  <= ~1 ulp of 1 absolute.
 __host__ __device__ __forceinline__ void sincos_q(double y, double *sn, double *cs) {
+#ifdef UNC_BUDGET_LIBM
+  sincos(y, sn, cs);
+  return;
+#endif
   const double km = fma(y, KTRIG[0], KTRIG[3]);
   const int n = UNC_LOINT(km);
   const double kf = km - KTRIG[3];
@@ -182,7 +200,7 @@ __host__ __device__ __forceinline__ void sincos_q(double y, double *sn, double *
 // 1/x for x in the normal range: hardware approximation (MUFU.RCP64H, ~20 bits) + two
 // Newton steps (4 DFMA) instead of the ~25-instruction IEEE division sequence; <= 1 ulp.
 __host__ __device__ __forceinline__ double rcp_fast(double x) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(UNC_BUDGET_IEEE_DIV)
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   double e = fma(-x, y, 1.0);
@@ -273,9 +291,14 @@ __host__ __device__ __forceinline__ bool ap_terms_fast_t(const DevParams &P, cpl
     const double iu02 = 1.0 / (P.mn_u0 * P.mn_u0);
     const cplx v = csqrt_pos(mk(1.0 + e1sq.re * iu02, e1sq.im * iu02));
     const cplx u = cscalef(mk(1.0 - v.re, -v.im), P.mn_u0);
-    const cplx D0 = csubf(cmulf(eta, E1.sh), cmulf(u, E1.ch));
     const cplx th = cscalef(crecipf(pa), 2.0 * w);       // 2/(kappa eta^2) = 2/(p + a^2)
-    const cplx g = cscalef(cmulf(th, cdivf(u, D0)), 0.5);
+    // u/Delta0.  |Delta0|^2 overflows at Re(eta) ~ 350 although Delta0 itself (and the
+    // reference's Smith division) stays finite up to ~709: for Re(eta) > 20, sinh = cosh =
+    // e^eta/2 to 2^-57, so Delta0 = e^eta (eta - u)/2 and u/Delta0 = 2 u e^-eta/(eta - u).
+    cplx ud;
+    if (eta.re > 20.0) ud = cscalef(cmulf(cdivf(u, csubf(eta, u)), E1.em), 2.0);
+    else ud = cdivf(u, csubf(cmulf(eta, E1.sh), cmulf(u, E1.ch)));
+    const cplx g = cscalef(cmulf(th, ud), 0.5);
 #pragma unroll
     for (int L = 0; L < 3; ++L) { co[L].k0 = th; co[L].cp = g; co[L].cm = g; }
     return true;

@@ -612,8 +612,12 @@ __host__ __device__ inline size_t smem_bytes(int np, int nacc, int na, int ZT) {
   size_t scratch = (size_t)UNC_WARPS * 3 * np * sizeof(cplx);  // de Hoog q,e,d per warp (aliases areas)
   b += areas > scratch ? areas : scratch;
   b += (size_t)np * ZT * sizeof(cplx);                // finint -> totlap
-  b += (size_t)ZT * (sizeof(double) + 2 * sizeof(int));  // z, lay, flags
-  return (b + 15) & ~(size_t)15;
+  b += (size_t)ZT * (2 * sizeof(double) + sizeof(int));  // z, stale masks (64 bit), lay
+  b = (b + 15) & ~(size_t)15;
+#ifdef UNC_BUDGET_SEQSUM
+  b += (size_t)UNC_WARPS * na * sizeof(cplx);           // every abscissa's value, per warp
+#endif
+  return b;
 }
 
 // Fast-path evaluation of one abscissa for the ZT z-values of a point-kernel tile, as a
@@ -675,10 +679,14 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
   const int np = P.np, nacc = P.nacc, G = P.G;
   const int na = P.nts_pad + P.gl_rounds * 32;
   const int ntiles = (J.nz + ZT - 1) / ZT;
-  const long long col = blockIdx.x / ntiles;
-  const int tile = (int)(blockIdx.x % ntiles);
+  // carry post-pass (ZT == 1 only): the CTA's point comes from a list instead of the launch grid
+  const int fix_mode = (ZT == 1) ? J.fix_mode : 0;
+  const long long fix_pt = fix_mode ? (long long)J.fix_list[blockIdx.x] : 0;
+  const long long col = fix_mode ? fix_pt / J.nz : blockIdx.x / ntiles;
+  const int tile = fix_mode ? (int)(fix_pt % J.nz) : (int)(blockIdx.x % ntiles);
   const int z0 = tile * ZT;
   const int nzt = min(ZT, J.nz - z0);
+  const unsigned long long pmask = (fix_mode == 1) ? J.fix_need[fix_pt] : ~0ull;   // p to evaluate
 
   // carve shared memory
   unsigned char *sp = smem_raw;
@@ -697,12 +705,17 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
   }
   cplx *s_fin = (cplx *)sp; sp += (size_t)np * ZT * sizeof(cplx);
   double *s_z = (double *)sp; sp += ZT * sizeof(double);
-  int *s_lay = (int *)sp; sp += ZT * sizeof(int);
-  int *s_flag = (int *)sp;
+  unsigned long long *s_mask = (unsigned long long *)sp; sp += ZT * sizeof(unsigned long long);
+  int *s_lay = (int *)sp;
+#ifdef UNC_BUDGET_SEQSUM
+  static_assert(ZT >= 1, "");
+  cplx *s_seq = (cplx *)(smem_raw + smem_bytes(np, nacc, na, ZT)) - (size_t)UNC_WARPS * na + (size_t)warp * na;
+#endif
 
-  const double tD = J.tD[col / J.tdiv];
-  const int sv = J.sv[col / J.tdiv];
-  const double rD = J.rD[col % J.rmod];
+  const long long tcol = col + J.col0;
+  const double tD = J.tD[tcol / J.tdiv];
+  const int sv = J.sv[tcol / J.tdiv];
+  const double rD = J.rD[tcol % J.rmod];
   const double tee = P.tee_mult * tD;
   const double arg = P.j0z[sv - 1] / rD;                      // driver.f90:120
   const double tscale = J.ts_scale ? J.ts_scale[col] : arg;  // driver.f90:121-126
@@ -713,7 +726,7 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
   if (tid < ZT) {
     s_z[tid] = (tid < nzt) ? zsrc[tid] : 0.0;
     s_lay[tid] = (tid < nzt) ? lsrc[tid] : 2;
-    s_flag[tid] = 0;
+    s_mask[tid] = 0ull;
   }
   for (int i = tid; i < np; i += UNC_THREADS) {
     // invlap.f90:166-170
@@ -743,6 +756,9 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       if (idx < P.N) {
         a = (P.ts_T[idx] * tscale) / 2.0;  // integration.f90:62
         w = P.ts_wc[idx] * (arg / 2.0);    // driver.f90:135,154 + Richardson (linear in tmp)
+#ifdef UNC_BUDGET_NEVILLE
+        w = arg / 2.0;                     // level weights applied in the sequential sums below
+#endif
       }
     } else {
       const int k = idx - P.nts_pad;
@@ -780,13 +796,15 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
   const double eta_max = fast_eta_max(P, lay_mask, zabs);
 
   for (int pi = warp; pi < np; pi += UNC_WARPS) {
+    if (!((pmask >> pi) & 1ull)) continue;
     cplx accT[ZT], accA[ZT], accB[ZT];
 #pragma unroll
     for (int i = 0; i < ZT; ++i) { accT[i] = mk(0, 0); accA[i] = mk(0, 0); accB[i] = mk(0, 0); }
     const cplx pp = T.p[pi], aux = T.aux[pi], aux2 = T.aux2[pi];
     const int nts_rounds = P.nts_pad / 32;
     // one abscissa per lane per round: tanh-sinh rounds first, then Gauss-Lobatto rounds
-    for (int i = 0; i < nts_rounds + rounds; ++i) {
+    // (a source of the carry post-pass only needs the Gauss-Lobatto part)
+    for (int i = (fix_mode == 1) ? nts_rounds : 0; i < nts_rounds + rounds; ++i) {
       const bool ts = i < nts_rounds;
       const int idx = ts ? i * 32 + lane : P.nts_pad + (i - nts_rounds) * 32 + lane;
       const bool valid = ts ? (idx < P.N) : (node0 + (i - nts_rounds) < nacc * G);
@@ -802,6 +820,9 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
               f[k] = mk(w * v.re, w * v.im);
             } else f[k] = mk(0.0, 0.0);
         }
+#ifdef UNC_BUDGET_SEQSUM
+        if (ZT == 1) s_seq[ts ? idx : P.N + node0 + (i - nts_rounds)] = f[0];
+#endif
         if (ts) {
 #pragma unroll
           for (int k = 0; k < ZT; ++k) accT[k] = caddf(accT[k], f[k]);
@@ -838,13 +859,61 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
         area_p[k * nacc + jA + 1] = mk(cur.re + accB[k].re, cur.im + accB[k].im);
       }
     }
+#ifdef UNC_BUDGET_SEQSUM
+    // error-budget build: redo the sums sequentially in the reference's order (driver.f90:135-157,
+    // 201-202) from the stored per-abscissa values, one lane per p
+    __syncwarp();
+    if (ZT == 1 && lane == 0) {
+#ifdef UNC_BUDGET_NEVILLE
+      // R level sums with their own weights, then extraptozero (integration.f90:192-237)
+      cplx c_[12], d_[12];
+      double x_[12];
+      const int R = P.R;
+      const double *lw = P.ts_lw;
+      for (int j = 1; j <= R; ++j) {
+        const int kv = P.ts_k - R + j, Nv = (1 << kv) - 1, step = 1 << (R - j);
+        cplx sum = mk(0.0, 0.0);
+        for (int m = 1; m <= Nv; ++m) sum = caddf(sum, cscalef(s_seq[m * step - 1], lw[m - 1]));
+        lw += Nv;
+        c_[j - 1] = d_[j - 1] = sum;
+        x_[j - 1] = 4.0 / (double)(1 << kv);
+      }
+      int ns = R;                    // hv decreasing: the smallest x is the last
+      cplx y = c_[ns - 1];
+      ns -= 1;
+      for (int m = 1; m <= R - 1; ++m) {
+        for (int i = 1; i <= R - m; ++i) {
+          const double dx = x_[i - 1] - x_[i + m - 1];
+          const cplx den = mk((c_[i].re - d_[i - 1].re) / dx, (c_[i].im - d_[i - 1].im) / dx);
+          d_[i - 1] = cscalef(den, x_[i + m - 1]);
+          c_[i - 1] = cscalef(den, x_[i - 1]);
+        }
+        cplx dy;
+        if (2 * ns < R - m) dy = c_[ns];
+        else { dy = d_[ns - 1]; ns -= 1; }
+        y = caddf(y, dy);
+      }
+      s_fin[pi * ZT] = (R > 1) ? y : c_[0];
+#else
+      cplx sum = mk(0.0, 0.0);
+      for (int m = 0; m < P.N; ++m) sum = caddf(sum, s_seq[m]);
+      s_fin[pi * ZT] = sum;
+#endif
+      for (int j = 0; j < nacc; ++j) {
+        cplx a_ = mk(0.0, 0.0);
+        for (int m = 0; m < G; ++m) a_ = caddf(a_, s_seq[P.N + j * G + m]);
+        area_p[j] = a_;
+      }
+    }
+    __syncwarp();
+#endif
   }
   __syncthreads();
 
   // ---- phase B: Wynn-epsilon per (p,z), totlap = finint + infint ---------------
   for (int k = tid; k < np * ZT; k += UNC_THREADS) {
     const int pi = k / ZT, zi = k - pi * ZT;
-    if (zi < nzt) {
+    if (zi < nzt && ((pmask >> pi) & 1ull)) {
       const double nan = __longlong_as_double(0x7ff8000000000000LL);
       const cplx lt = T.lt[pi];
       cplx series[UNC_MAX_NACC];
@@ -857,13 +926,28 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       }
       cplx infint = mk(0.0, 0.0);
       if (any) infint = wynn_any(series, nacc);
-      else atomicOr(&s_flag[zi], 1);
+      else {
+        atomicOr(&s_mask[zi], 1ull << pi);
+        if (fix_mode == 2) {
+          // driver.f90:209-211: infint(p,z) keeps the value of the last (t,r) that set it
+          const int src = J.fix_src[(size_t)blockIdx.x * np + pi];
+          if (src >= 0) {
+            const double *v = J.fix_val + ((size_t)src * np + pi) * 2;
+            infint = mk(v[0], v[1]);
+          }
+        }
+      }
+      if (fix_mode == 1) {
+        double *v = J.fix_val + ((size_t)blockIdx.x * np + pi) * 2;
+        v[0] = infint.re; v[1] = infint.im;
+      }
       cplx fin = s_fin[k];
       fin = is_finite_c(fin) ? fin * lt : mk(nan, nan);
       s_fin[k] = fin + infint;  // totlap, driver.f90:216
     }
   }
   __syncthreads();
+  if (fix_mode == 1) return;
 
   // ---- phase C: de Hoog inversion of value and log-time derivative ------------
   cplx *scr = s_area + (size_t)warp * 3 * np;
@@ -873,10 +957,14 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
                            scr + 2 * np, lane);
     if (lane == 0) {
       const long long o = col * (long long)J.nz + z0 + zi;
-      if (deriv) J.ds[o] = v * tD;  // driver.f90:228
+      if (fix_mode == 2) {
+        if (deriv) { J.fix_ds[blockIdx.x] = v * tD; if (J.ds) J.ds[o] = v * tD; }
+        else { J.fix_s[blockIdx.x] = v; if (J.s) J.s[o] = v; }
+      } else if (deriv) J.ds[o] = v * tD;  // driver.f90:228
       else {
         J.s[o] = v;
-        if (J.flags) J.flags[o] = s_flag[zi];
+        if (J.flags) J.flags[o] = s_mask[zi] != 0ull ? 1 : 0;
+        if (J.smask) J.smask[o] = s_mask[zi];
       }
     }
     __syncwarp();
@@ -941,9 +1029,10 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
   }
   int *s_misc = (int *)sp;  // [0] layer mask, [1] bits of max|z| (float)
 
-  const double tD = J.tD[col / J.tdiv];
-  const int sv = J.sv[col / J.tdiv];
-  const double rD = J.rD[col % J.rmod];
+  const long long tcol = col + J.col0;
+  const double tD = J.tD[tcol / J.tdiv];
+  const int sv = J.sv[tcol / J.tdiv];
+  const double rD = J.rD[tcol % J.rmod];
   const double tee = P.tee_mult * tD;
   const double arg = P.j0z[sv - 1] / rD;                      // driver.f90:120
   const double tscale = J.ts_scale ? J.ts_scale[col] : arg;  // driver.f90:121-126
@@ -1023,7 +1112,9 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
   // ---- phase A+B per p -----------------------------------------------------------
   StageEnt *stage = s_stage + warp * 32;
   int *okv = s_ok + warp * 32;
-  int stale = 0;  // bit k: z-slot k had an all-zero/NaN series for some p
+  unsigned long long stale[ZL];  // per z-slot: bit p = all-zero/NaN series for that p
+#pragma unroll
+  for (int k = 0; k < ZL; ++k) stale[k] = 0ull;
   for (int pi = warp; pi < np; pi += UNC_WARPS) {
     const cplx pp = T.p[pi], aux = T.aux[pi], aux2 = T.aux2[pi];
     cplx series[ZL][UNC_MAX_NACC];
@@ -1108,7 +1199,7 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
       }
       cplx infint = mk(0.0, 0.0);
       if (any) infint = wynn_any(series[k], nacc);
-      else stale |= 1 << k;
+      else stale[k] |= 1ull << pi;
       cplx f = fin[k];
       f = is_finite_c(f) ? f * lt : mk(nan, nan);
       s_tot[(size_t)pi * ZB + 32 * k + lane] = f + infint;
@@ -1116,13 +1207,13 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
   }
   // per-z stale flag: OR over the warps via shared memory
   __syncthreads();
-  int *s_flag = (int *)s_scr;  // stage no longer needed
-  if (tid < ZB) s_flag[tid] = 0;
+  unsigned long long *s_flag = (unsigned long long *)s_scr;  // stage no longer needed
+  if (tid < ZB) s_flag[tid] = 0ull;
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < ZL; ++k) if (stale & (1 << k)) atomicOr(&s_flag[32 * k + lane], 1);
+  for (int k = 0; k < ZL; ++k) if (stale[k]) atomicOr(&s_flag[32 * k + lane], stale[k]);
   __syncthreads();
-  int myflag[ZL];
+  unsigned long long myflag[ZL];
 #pragma unroll
   for (int k = 0; k < ZL; ++k) myflag[k] = s_flag[32 * k + lane];
   __syncthreads();
@@ -1133,10 +1224,10 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
     const int zi = job >> 1, deriv = job & 1;
     double v = dehoog_warp(P, s_tot + zi, ZB, deriv ? T.p : nullptr, tD, tee, scr, scr + np,
                            scr + 2 * np, lane);
-    int fl = 0;
+    unsigned long long fl = 0ull;
 #pragma unroll
     for (int k = 0; k < ZL; ++k) {
-      int f = __shfl_sync(0xffffffffu, myflag[k], zi & 31);
+      unsigned long long f = __shfl_sync(0xffffffffu, myflag[k], zi & 31);
       if ((zi >> 5) == k) fl = f;
     }
     if (lane == 0) {
@@ -1144,7 +1235,8 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
       if (deriv) J.ds[o] = v * tD;  // driver.f90:228
       else {
         J.s[o] = v;
-        if (J.flags) J.flags[o] = fl;
+        if (J.flags) J.flags[o] = fl != 0ull ? 1 : 0;
+        if (J.smask) J.smask[o] = fl;
       }
     }
     __syncwarp();
@@ -1182,62 +1274,6 @@ __device__ __forceinline__ long long prof_clock() {
 #define PROF_ADD(i)
 #endif
 
-struct StageEnt4 {
-  cplx eta;
-  Coef co[3];
-  cplx sp, sm;  // exp(+eta*D), exp(-eta*D), D = z spacing between a lane's slots
-};
-
-__host__ __device__ inline size_t grid4_smem_bytes(int np, int na_seq, int NW) {
-  size_t b = 0;
-  b += (size_t)4 * np * sizeof(cplx);
-  b += (size_t)2 * na_seq * sizeof(double);
-  size_t stage = (size_t)NW * 32 * sizeof(StageEnt4) + (size_t)NW * 32 * sizeof(int);
-  size_t scratch = (size_t)NW * 3 * np * sizeof(cplx);
-  b += stage > scratch ? stage : scratch;
-  b += 2 * 128 * sizeof(int) + 64;
-  return (b + 15) & ~(size_t)15;
-}
-
-// ZMASK: bit k set = the coefficients of slot k have k0 == 0 exactly (layers below/above the
-// screen of models 1,2,3,5): the four products are then accumulated straight into acc[k]
-// (4 FMA per component) instead of forming f = k0 + ... first and adding it (4 FMA + 1 add).
-template <int ZMASK>
-__device__ __forceinline__ void eval4_recur(const StageEnt4 &e, const Coef &c0, const Coef &c1,
-                                            const Coef &c2, const Coef &c3, double z0, cplx *acc) {
-  double ep, em, cc, ss, s, cs;
-  int kk;
-  exp_pm_core(e.eta.re * z0, &ep, &em, &cc, &ss, &kk);
-  sincos_q(e.eta.im * z0, &s, &cs);
-  cplx Ep = mk(ep * cs, ep * s), Em = mk(em * cs, -(em * s));
-  const Coef *cf[4] = {&c0, &c1, &c2, &c3};
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const Coef &c = *cf[k];
-    if (ZMASK & (1 << k)) {
-      double fr = fma(c.cp.re, Ep.re, acc[k].re);
-      fr = fma(-c.cp.im, Ep.im, fr);
-      fr = fma(c.cm.re, Em.re, fr);
-      fr = fma(-c.cm.im, Em.im, fr);
-      double fi = fma(c.cp.re, Ep.im, acc[k].im);
-      fi = fma(c.cp.im, Ep.re, fi);
-      fi = fma(c.cm.re, Em.im, fi);
-      fi = fma(c.cm.im, Em.re, fi);
-      acc[k] = mk(fr, fi);
-    } else {
-      double fr = fma(c.cp.re, Ep.re, c.k0.re);
-      fr = fma(-c.cp.im, Ep.im, fr);
-      fr = fma(c.cm.re, Em.re, fr);
-      fr = fma(-c.cm.im, Em.im, fr);
-      double fi = fma(c.cp.re, Ep.im, c.k0.im);
-      fi = fma(c.cp.im, Ep.re, fi);
-      fi = fma(c.cm.re, Em.im, fi);
-      fi = fma(c.cm.im, Em.re, fi);
-      acc[k] = mk(acc[k].re + fr, acc[k].im + fi);
-    }
-    if (k < 3) { Ep = cmulf(Ep, e.sp); Em = cmulf(Em, e.sm); }
-  }
-}
 
 // ---------------------------------------------------------------------------
 // Eight z-slots per lane, two Laplace parameters per warp (lh_grid8_kernel below).
@@ -1342,86 +1378,6 @@ __device__ __noinline__ int hot8_chunk(const StageEnt8 *stage, int cnt, double z
   return seg;
 }
 
-// The hot loop as separate functions: the persistent kernel around it keeps ~100 registers
-// of long-lived state, and inlined there the loop was compiled with address
-// rematerialisation (S2R/R2UR) and extra loads; as a call it gets its own register
-// allocation (the isolated loop runs at 98% of the FP64 pipe, tools/micro/hotloop_bench.cu).
-// acc lives in the caller's local memory only across the call.
-#ifndef UNC_HOT_UNROLL
-#define UNC_HOT_UNROLL 1
-#endif
-constexpr int kHotUnroll = UNC_HOT_UNROLL;
-template <bool K0Z>
-__device__ __noinline__ void hot_run_same(const StageEnt4 *stage, int j, int jend, double z0, int L,
-                                          cplx *acc_io) {
-  cplx acc[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) acc[k] = acc_io[k];
-#pragma unroll kHotUnroll
-  for (; j < jend; ++j) {
-    const StageEnt4 &e = stage[j];
-    const Coef c = e.co[L];
-    eval4_recur<K0Z ? 15 : 0>(e, c, c, c, c, z0, acc);
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) acc_io[k] = acc[k];
-}
-
-__device__ __noinline__ void hot_run_mixed(const StageEnt4 *stage, int j, int jend, double z0,
-                                           int Lpack, cplx *acc_io) {
-  cplx acc[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) acc[k] = acc_io[k];
-  const int l0 = Lpack & 3, l1 = (Lpack >> 2) & 3, l2 = (Lpack >> 4) & 3, l3 = (Lpack >> 6) & 3;
-#pragma unroll kHotUnroll
-  for (; j < jend; ++j) {
-    const StageEnt4 &e = stage[j];
-    eval4_recur<0>(e, e.co[l0], e.co[l1], e.co[l2], e.co[l3], z0, acc);
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) acc_io[k] = acc[k];
-}
-
-// One slot (KX) with lane-dependent layers, the other three on the common layer L: the usual
-// case of a z-block that straddles a layer boundary (z ascending, so the boundary falls in
-// one slot).  Three broadcast loads for the common coefficients plus three per-lane ones,
-// instead of twelve per-lane loads and four coefficient sets in registers.
-template <int KX, bool K0Z>
-__device__ __noinline__ void hot_run_exc(const StageEnt4 *stage, int j, int jend, double z0, int L,
-                                         int Lx, cplx *acc_io) {
-  cplx acc[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) acc[k] = acc_io[k];
-  for (; j < jend; ++j) {
-    const StageEnt4 &e = stage[j];
-    const Coef c = e.co[L];
-    const Coef cx = e.co[Lx];
-    eval4_recur<K0Z ? (15 & ~(1 << KX)) : 0>(e, KX == 0 ? cx : c, KX == 1 ? cx : c, KX == 2 ? cx : c, KX == 3 ? cx : c, z0, acc);
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) acc_io[k] = acc[k];
-}
-
-// Per-(a,p) terms written straight into the shared-memory stage entry.  A separate function
-// on purpose: inlined into the persistent kernel it was compiled under that kernel's
-// register pressure, spilled ~1 KB per call to L2-backed local memory and cost 2/3 of the
-// step (phase ablation, tools/micro/run_variants.sh); as a call it has its own allocation.
-__device__ __noinline__ int ap_terms_stage(const DevParams &P, cplx p, cplx aux, cplx aux2, double a2,
-                                           double w, int lay_mask, double eta_max, bool zuni,
-                                           double Dz, StageEnt4 *out) {
-  StageEnt4 e;
-  const bool ok = ap_terms_fast(P, p, aux, aux2, a2, w, lay_mask, eta_max, &e.eta, e.co);
-  if (zuni && ok) {
-    const cbundle S = cexp_bundle(e.eta.re * Dz, e.eta.im * Dz);
-    e.sp = S.ep;
-    e.sm = S.em;
-  } else {
-    e.sp = mk(1.0, 0.0);
-    e.sm = mk(1.0, 0.0);
-  }
-  *out = e;
-  return ok ? 1 : 0;
-}
 
 // The same for the eight-slot kernel: also exp(+-eta*Dz*kx) for the exception slot kx (>= 1).
 template <int MODEL>
@@ -1606,393 +1562,13 @@ __host__ __device__ inline size_t grid8_smem_bytes(int np, int na_seq, int NW) {
   size_t stage = (size_t)NW * 32 * sizeof(StageEnt8) + (size_t)NW * 32 * sizeof(int);
   size_t scratch = (size_t)NW * 3 * np * sizeof(cplx);
   b += stage > scratch ? stage : scratch;
-  b += 2 * 128 * sizeof(int) + 64;
+  b += 2 * 128 * sizeof(unsigned long long) + 64;
   return (b + 15) & ~(size_t)15;
 }
 
 #ifndef UNC_GRID4_MINB
 #define UNC_GRID4_MINB 2
 #endif
-template <int NW>
-__global__ void __launch_bounds__(NW * 32, UNC_GRID4_MINB)
-lh_grid4_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job J,
-                cplx *__restrict__ g_tot, unsigned int *__restrict__ g_counter) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int ZL = 4, ZB = 128;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int np = P.np, nacc = P.nacc, G = P.G, N = P.N;
-  const int NA = N + nacc * G;
-  const int na_seq = (NA + 31) & ~31;
-  const int nzb = (J.nz + ZB - 1) / ZB;
-  const long long nitems = J.ncol * (long long)nzb;
-
-  unsigned char *sp = smem_raw;
-  PTab T;
-  T.p = (cplx *)sp; sp += np * sizeof(cplx);
-  T.lt = (cplx *)sp; sp += np * sizeof(cplx);
-  T.aux = (cplx *)sp; sp += np * sizeof(cplx);
-  T.aux2 = (cplx *)sp; sp += np * sizeof(cplx);
-  double *s_a2 = (double *)sp; sp += na_seq * sizeof(double);
-  double *s_wj = (double *)sp; sp += na_seq * sizeof(double);
-  StageEnt4 *s_stage = (StageEnt4 *)sp;
-  int *s_ok = (int *)(sp + (size_t)NW * 32 * sizeof(StageEnt4));
-  cplx *s_scr = (cplx *)sp;
-  {
-    size_t stage = (size_t)NW * 32 * sizeof(StageEnt4) + (size_t)NW * 32 * sizeof(int);
-    size_t scratch = (size_t)NW * 3 * np * sizeof(cplx);
-    sp += stage > scratch ? stage : scratch;
-  }
-  int *s_flag = (int *)sp; sp += 2 * 128 * sizeof(int);   // stale flags per z, [buffer][z]
-  int *s_misc = (int *)sp;  // [0] layer mask, [1] max|z| bits, [2] uniform-z flag, [3] item, [6..7] D, [8] job counter
-  cplx *tot_base = g_tot + (size_t)blockIdx.x * 2 * np * ZB;  // this CTA's two totlap slots [p][z]
-
-  // Software pipeline over work items: round i runs the np quadrature jobs ("p-jobs") of
-  // item i AND the de Hoog jobs ("D-jobs", 32 inversions each, one per lane) of item i-1 out
-  // of one job pool that the warps drain through a shared-memory counter.  The small D-jobs
-  // come last, so the warps that run out of p-jobs invert the previous item's totlap while
-  // the others finish: no separate de Hoog phase with every warp stalled on its q-d table,
-  // and the end-of-round barrier waits for a D-job at most, not for a p-job.
-  int buf = 0;
-  bool have_prev = false, dry = false;
-  long long prev_col = 0;
-  int prev_z0 = 0, prev_nzv = 0;
-  double prev_tD = 0.0;
-  PROF_T0();
-  for (;;) {
-    __syncthreads();   // every job of the previous round is complete
-    PROF_ADD(0);
-    if (tid == 0) {
-      if (!dry) s_misc[3] = (int)atomicAdd(g_counter, 1u);
-      s_misc[8] = 0;
-    }
-    __syncthreads();
-    const long long item = (unsigned int)s_misc[3];
-    const bool have_cur = item < nitems;
-    if (!have_cur) dry = true;
-    if (!have_cur && !have_prev) {
-      // the last CTA to finish re-arms both counters, so every launch (and every profiler
-      // replay of a launch) starts from zero without a host-side memset
-      if (tid == 0) {
-        __threadfence();
-        if (atomicAdd(g_counter + 1, 1u) == gridDim.x - 1) {
-          g_counter[0] = 0u;
-          g_counter[1] = 0u;
-          __threadfence();
-        }
-      }
-      break;
-    }
-    cplx *tot = tot_base + (size_t)buf * np * ZB;
-    const cplx *tot_prev = tot_base + (size_t)(buf ^ 1) * np * ZB;
-    int *flag_cur = s_flag + buf * 128;
-    const int *flag_prev = s_flag + (buf ^ 1) * 128;
-
-    const long long col = have_cur ? item / nzb : 0;
-    const int z0 = have_cur ? (int)(item % nzb) * ZB : 0;
-    const int nzv = have_cur ? min(ZB, J.nz - z0) : 0;
-    const double tD = J.tD[col / J.tdiv];
-    const int sv = J.sv[col / J.tdiv];
-    const double rD = J.rD[col % J.rmod];
-    const double tee = P.tee_mult * tD;
-    const double arg = P.j0z[sv - 1] / rD;                      // driver.f90:120
-    const double tscale = J.ts_scale ? J.ts_scale[col] : arg;  // driver.f90:121-126
-    const long long zbase = (J.zstride ? col * (long long)J.nz : 0) + z0;
-    double myz[ZL];
-    int mylay[ZL];
-    bool zvalid[ZL];
-#pragma unroll
-    for (int k = 0; k < ZL; ++k) {
-      const int zi = lane + 32 * k;
-      zvalid[k] = zi < nzv;
-      myz[k] = zvalid[k] ? J.zD[zbase + zi] : 0.0;
-      mylay[k] = zvalid[k] ? J.zLay[zbase + zi] : 0;
-    }
-
-    // ---- prologue (tables of the current item) -----------------------------------
-    if (have_cur) {
-      if (tid < ZB) flag_cur[tid] = 0;
-      for (int i = tid; i < np; i += NW * 32) {
-        const double PI = 3.141592653589793;
-        double sigma = P.alpha - P.log_tol / (2.0 * tee);   // invlap.f90:166-170
-        cplx p = mk(sigma, PI * (double)i / tee);
-        T.p[i] = p;
-        T.lt[i] = laptime_dev(P, p);
-        cplx aux = mk(0.0, 0.0), aux2 = mk(0.0, 0.0);
-        if (P.model == 3) {
-          for (int m = 0; m < P.moench_M; ++m) aux = aux + 1.0 / (1.0 + p * (1.0 / P.moench_gamma[m]));
-        } else if (P.model == 2) {
-          cplx xi = P.rDw * csqrt_g(p);
-          cplx K[2];
-          cbesk01_dev(xi, K);
-          aux = 2.0 / (p * P.CDw * K[0] + xi * K[1]);
-          aux2 = p * P.tDb + 1.0;
-        }
-        T.aux[i] = aux;
-        T.aux2[i] = aux2;
-      }
-      for (int idx = tid; idx < na_seq; idx += NW * 32) {
-        double a = 0.0, w = 0.0;
-        if (idx < N) {
-          a = (P.ts_T[idx] * tscale) / 2.0;  // integration.f90:62
-          w = P.ts_wc[idx] * (arg / 2.0);    // driver.f90:135,154 + Richardson (linear in tmp)
-        } else if (idx < NA) {
-          const int node = idx - N;
-          const int j = node / G, m = node - j * G;
-          const double lob = P.j0z[sv + j - 1] / rD;  // driver.f90:188-193
-          const double hib = P.j0z[sv + j] / rD;
-          const double width = hib - lob;
-          a = fma(width, P.gl_x[m], hib + lob) / 2.0;
-          w = P.gl_w[m] * (width / 2.0);
-        }
-        s_a2[idx] = a * a;
-        s_wj[idx] = (w != 0.0) ? w * (a * j0_dev(a * rD)) : 0.0;  // laplace_hankel_solutions.f90:118
-      }
-      if (warp == 0) {
-        int m = 0;
-        float za = 0.f;
-#pragma unroll
-        for (int k = 0; k < ZL; ++k)
-          if (zvalid[k]) { m |= 1 << (mylay[k] - 1); za = fmaxf(za, (float)fabs(myz[k]) * 1.0000002f); }
-        for (int o = 16; o > 0; o >>= 1) {
-          m |= __shfl_xor_sync(0xffffffffu, m, o);
-          za = fmaxf(za, __shfl_xor_sync(0xffffffffu, za, o));
-        }
-        // equally spaced slots?  D from lane 0 (slots 0,1 are always valid when nz >= 64)
-        const double D = __shfl_sync(0xffffffffu, myz[1] - myz[0], 0);
-        const double tol = 4.0 * 2.220446049250313e-16 * (double)za;
-        bool uni = __shfl_sync(0xffffffffu, (int)(zvalid[0] && zvalid[1]), 0) != 0;
-#pragma unroll
-        for (int k = 0; k + 1 < ZL; ++k)
-          if (zvalid[k] && zvalid[k + 1] && !(fabs((myz[k + 1] - myz[k]) - D) <= tol)) uni = false;
-        uni = __all_sync(0xffffffffu, uni);
-        if (lane == 0) {
-          s_misc[0] = m;
-          s_misc[1] = __float_as_int(za);
-          s_misc[2] = uni ? 1 : 0;
-          *(double *)(s_misc + 6) = D;
-        }
-      }
-    }
-    __syncthreads();
-    PROF_ADD(1);
-    const int lay_mask = have_cur ? s_misc[0] : 1;
-    const double eta_max = fast_eta_max(P, lay_mask, (double)__int_as_float(s_misc[1]));
-    const bool zuni = s_misc[2] != 0;
-    const double Dz = *(double *)(s_misc + 6);
-    const int L0 = __ffs(lay_mask) - 1;
-    int myL[ZL];
-#pragma unroll
-    for (int k = 0; k < ZL; ++k) {
-      if (!zvalid[k]) {                 // padding slots mimic a present layer / the uniform grid
-        mylay[k] = L0 + 1;
-        myz[k] = zuni ? myz[0] + k * Dz : 0.5;
-        if (!zvalid[0]) myz[k] = 0.5;
-      }
-      myL[k] = mylay[k] - 1;
-    }
-    const int Lpack = myL[0] | (myL[1] << 2) | (myL[2] << 4) | (myL[3] << 6);
-    const bool same_layer = (lay_mask & (lay_mask - 1)) == 0;   // one layer in the whole block
-    // slots whose lanes are not all on the layer of (slot 0, lane 0); exactly one such slot
-    // gets the cheaper "exception" loop
-    const int Lc = __shfl_sync(0xffffffffu, myL[0], 0);
-    int offmask = 0;
-#pragma unroll
-    for (int k = 0; k < ZL; ++k)
-      if (!__all_sync(0xffffffffu, myL[k] == Lc)) offmask |= 1 << k;
-    const int kx = (offmask != 0 && (offmask & (offmask - 1)) == 0) ? __ffs(offmask) - 1 : -1;
-    int Lx = myL[0];
-#pragma unroll
-    for (int k = 1; k < ZL; ++k) if (k == kx) Lx = myL[k];
-    // k0 of the common layer is exactly zero below/above the screen of the Hantush-type models
-    const bool k0z = (P.model == 1 || P.model == 2 || P.model == 3 || P.model == 5) && Lc != 1;
-
-    const int njobs_p = have_cur ? np : 0;
-    const int njobs_d = have_prev ? (2 * prev_nzv + 31) / 32 : 0;
-    StageEnt4 *stage = s_stage + warp * 32;
-    int *okv = s_ok + warp * 32;
-    for (;;) {
-      int job = 0;
-      if (lane == 0) job = atomicAdd(&s_misc[8], 1);
-      job = __shfl_sync(0xffffffffu, job, 0);
-      if (job >= njobs_p + njobs_d) break;
-      if (job >= njobs_p) {
-        // ---- D-job: de Hoog for 32 (z, value|derivative) pairs of the PREVIOUS item ------
-        const int idx = (job - njobs_p) * 32 + lane;
-        if (idx < 2 * prev_nzv) {
-          const int deriv = idx >= prev_nzv ? 1 : 0;
-          const int zi = idx - deriv * prev_nzv;
-          const double ptee = P.tee_mult * prev_tD;
-#ifdef UNC_SKIP_DEHOOG
-          double v = tot_prev[zi].re;
-#else
-          double v = dehoog_lane(P, tot_prev + zi, ZB, deriv != 0, prev_tD, ptee);
-#endif
-          const long long o = prev_col * (long long)J.nz + prev_z0 + zi;
-          if (deriv) J.ds[o] = v * prev_tD;  // driver.f90:228
-          else {
-            J.s[o] = v;
-            if (J.flags) J.flags[o] = flag_prev[zi];
-          }
-        }
-        __syncwarp();
-        PROF_ADD(6);
-        continue;
-      }
-      // ---- p-job: Hankel quadrature + Wynn for one Laplace parameter, 128 z ----------
-      const int pi = job;
-      int stale = 0;
-      const cplx pp = T.p[pi], aux = T.aux[pi], aux2 = T.aux2[pi];
-      cplx series[ZL][UNC_MAX_NACC];
-      cplx acc[ZL], fin[ZL];
-#pragma unroll
-      for (int k = 0; k < ZL; ++k) { acc[k] = mk(0.0, 0.0); fin[k] = mk(0.0, 0.0); }
-      int seg = 0;
-      int next_b = N;
-      // Wynn only uses the areas before the first non-finite one (integration.f90:140-160) and
-      // driver.f90:209 only asks whether SOME area is finite and non-zero.  Once that is settled
-      // for every z of the warp (dead: a non-finite area seen; anyf: a finite non-zero one seen)
-      // the remaining, ever more expensive, overflowing abscissae cannot change the result.
-      const cplx lt_chk = T.lt[pi];
-      const bool lt_ok = is_finite_fastc(lt_chk) && (lt_chk.re != 0.0 || lt_chk.im != 0.0);
-      int dead = 0, anyf = 0;
-      bool done = false;
-      // (measured: starting half of the warps with a half chunk to de-synchronise the
-      // ap_terms / hot-loop phases of the warps sharing a scheduler is 2% SLOWER)
-      for (int base = 0; base < NA && !done; base += 32) {
-        int ok = 1;
-        {
-          const int idx = base + lane;
-          if (idx < NA)
-            ok = ap_terms_stage(P, pp, aux, aux2, s_a2[idx], s_wj[idx], lay_mask, eta_max, zuni, Dz,
-                                &stage[lane]);
-          okv[lane] = ok;
-        }
-        const bool all_ok = __all_sync(0xffffffffu, ok);
-        __syncwarp();
-        PROF_ADD(2);
-        const int cnt = min(32, NA - base);
-        int j = 0;
-        while (j < cnt) {
-          const int jend = min(cnt, next_b - base);
-          if (all_ok && zuni) {
-            // hot loop: one exp+sincos for slot 0, complex-multiply recurrence for slots 1..3
-#ifndef UNC_SKIP_HOT
-            if (same_layer) {
-              if (k0z) hot_run_same<true>(stage, j, jend, myz[0], myL[0], acc);
-              else hot_run_same<false>(stage, j, jend, myz[0], myL[0], acc);
-            } else if (kx >= 0 && k0z) {
-              if (kx == 3) hot_run_exc<3, true>(stage, j, jend, myz[0], Lc, Lx, acc);
-              else if (kx == 2) hot_run_exc<2, true>(stage, j, jend, myz[0], Lc, Lx, acc);
-              else if (kx == 1) hot_run_exc<1, true>(stage, j, jend, myz[0], Lc, Lx, acc);
-              else hot_run_exc<0, true>(stage, j, jend, myz[0], Lc, Lx, acc);
-            } else if (kx >= 0) {
-              if (kx == 3) hot_run_exc<3, false>(stage, j, jend, myz[0], Lc, Lx, acc);
-              else if (kx == 2) hot_run_exc<2, false>(stage, j, jend, myz[0], Lc, Lx, acc);
-              else if (kx == 1) hot_run_exc<1, false>(stage, j, jend, myz[0], Lc, Lx, acc);
-              else hot_run_exc<0, false>(stage, j, jend, myz[0], Lc, Lx, acc);
-            } else hot_run_mixed(stage, j, jend, myz[0], Lpack, acc);
-#endif
-            j = jend;
-          } else {
-            for (; j < jend; ++j) {
-              if (okv[j]) {
-#pragma unroll
-                for (int k = 0; k < ZL; ++k)
-                  acc[k] = caddf(acc[k], eval_z_fast(stage[j].eta, stage[j].co[myL[k]], myz[k]));
-              } else {
-                const int id = base + j;
-                const double w = s_wj[id];
-#pragma unroll
-                for (int k = 0; k < ZL; ++k) {
-                  cplx v = soln_literal_one(P, T, pi, s_a2[id], myz[k], mylay[k]);
-                  acc[k] = caddf(acc[k], mk(w * v.re, w * v.im));
-                }
-              }
-            }
-          }
-          const bool seg_end = (base + j == next_b && next_b < NA);
-          if (seg >= 1 && lt_ok && (seg_end || !all_ok)) {
-            // at an interval end: record its fate; inside an interval that already went
-            // non-finite for everybody (only looked at after chunks with literal nodes): stop
-            int cur_bad = 0;
-#pragma unroll
-            for (int k = 0; k < ZL; ++k) {
-              const bool f = is_finite_fastc(acc[k]);
-              if (!f) cur_bad |= 1 << k;
-              if (seg_end && f && (acc[k].re != 0.0 || acc[k].im != 0.0)) anyf |= 1 << k;
-            }
-            if (seg_end) dead |= cur_bad;
-            const int settled = (dead | cur_bad) & anyf;
-            if (__all_sync(0xffffffffu, settled == (1 << ZL) - 1)) {
-              const double nanv = __longlong_as_double(0x7ff8000000000000LL);
-#pragma unroll
-              for (int k = 0; k < ZL; ++k) {
-                if (seg_end) series[k][seg - 1] = acc[k];
-                for (int jj = seg_end ? seg : seg - 1; jj < nacc; ++jj) series[k][jj] = mk(nanv, nanv);
-                acc[k] = mk(nanv, nanv);
-              }
-              seg = nacc;   // the final store below rewrites series[nacc-1] with NaN
-              done = true;
-              break;
-            }
-          }
-          if (seg_end) {
-#pragma unroll
-            for (int k = 0; k < ZL; ++k) {
-              if (seg == 0) fin[k] = acc[k]; else series[k][seg - 1] = acc[k];
-              acc[k] = mk(0.0, 0.0);
-            }
-            seg += 1;
-            next_b += G;
-          }
-        }
-        __syncwarp();
-        PROF_ADD(3);
-      }
-#pragma unroll
-      for (int k = 0; k < ZL; ++k) { if (seg == 0) fin[k] = acc[k]; else series[k][seg - 1] = acc[k]; }
-      const double nan = __longlong_as_double(0x7ff8000000000000LL);
-      const cplx lt = T.lt[pi];
-      int live = 0;
-#pragma unroll
-      for (int k = 0; k < ZL; ++k) {
-        bool any = false;
-        for (int j = 0; j < nacc; ++j) {
-          cplx a = series[k][j];
-          const bool fin_a = is_finite_fastc(a);
-          a = fin_a ? a * lt : mk(nan, nan);
-          series[k][j] = a;
-          if (fin_a && (a.re != 0.0 || a.im != 0.0)) any = true;  // abs(GLarea) > 0, driver.f90:209
-        }
-        if (any) live |= 1 << k;
-        else stale |= 1 << k;
-      }
-      cplx infint[ZL];
-#pragma unroll
-      for (int k = 0; k < ZL; ++k) infint[k] = mk(0.0, 0.0);
-#if defined(UNC_SKIP_WYNN)
-#pragma unroll
-      for (int k = 0; k < ZL; ++k) if (live & (1 << k)) infint[k] = series[k][0];
-#else
-#pragma unroll
-      for (int k = 0; k < ZL; ++k) if (live & (1 << k)) infint[k] = wynn_grid(series[k], nacc);
-#endif
-#pragma unroll
-      for (int k = 0; k < ZL; ++k) {
-        cplx f = fin[k];
-        f = is_finite_fastc(f) ? f * lt : mk(nan, nan);
-        tot[(size_t)pi * ZB + 32 * k + lane] = f + infint[k];   // totlap, driver.f90:216
-      }
-#pragma unroll
-      for (int k = 0; k < ZL; ++k) if (stale & (1 << k)) atomicOr(&flag_cur[32 * k + lane], 1);
-      PROF_ADD(4);
-    }
-    PROF_ADD(5);
-    have_prev = have_cur;
-    prev_col = col; prev_z0 = z0; prev_nzv = nzv; prev_tD = tD;
-    buf ^= 1;
-  }
-}
 
 // ---------------------------------------------------------------------------
 // Grid kernel, second generation: the job-pool structure of lh_grid4_kernel with EIGHT z-slots
@@ -2032,7 +1608,7 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
     size_t scratch = (size_t)NW * 3 * np * sizeof(cplx);
     sp += stage > scratch ? stage : scratch;
   }
-  int *s_flag = (int *)sp; sp += 2 * 128 * sizeof(int);   // stale flags per z, [buffer][z]
+  unsigned long long *s_flag = (unsigned long long *)sp; sp += 2 * 128 * sizeof(unsigned long long);   // stale masks (bit p) per z, [buffer][z]
   int *s_misc = (int *)sp;  // [0] layer mask, [1] max|z| bits, [2] uniform-z flag, [3] item, [6..7] D, [8] job counter
   cplx *tot_base = g_tot + (size_t)blockIdx.x * 2 * np * ZB;  // this CTA's two totlap slots [p][z]
 
@@ -2075,15 +1651,16 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
     }
     cplx *tot = tot_base + (size_t)buf * np * ZB;
     const cplx *tot_prev = tot_base + (size_t)(buf ^ 1) * np * ZB;
-    int *flag_cur = s_flag + buf * 128;
-    const int *flag_prev = s_flag + (buf ^ 1) * 128;
+    unsigned long long *flag_cur = s_flag + buf * 128;
+    const unsigned long long *flag_prev = s_flag + (buf ^ 1) * 128;
 
     const long long col = have_cur ? item / nzb : 0;
     const int z0 = have_cur ? (int)(item % nzb) * ZB : 0;
     const int nzv = have_cur ? min(ZB, J.nz - z0) : 0;
-    const double tD = J.tD[col / J.tdiv];
-    const int sv = J.sv[col / J.tdiv];
-    const double rD = J.rD[col % J.rmod];
+    const long long tcol = col + J.col0;
+    const double tD = J.tD[tcol / J.tdiv];
+    const int sv = J.sv[tcol / J.tdiv];
+    const double rD = J.rD[tcol % J.rmod];
     const double tee = P.tee_mult * tD;
     const double arg = P.j0z[sv - 1] / rD;                      // driver.f90:120
     const double tscale = J.ts_scale ? J.ts_scale[col] : arg;  // driver.f90:121-126
@@ -2102,7 +1679,7 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
     // ---- prologue (tables of the current item) -----------------------------------
     PROF_ADD(8);
     if (have_cur) {
-      if (tid < ZB) flag_cur[tid] = 0;
+      if (tid < ZB) flag_cur[tid] = 0ull;
       item_tables(P, T, s_a2, s_wj, tD, sv, rD, tscale, tid, NW * 32);
       PROF_ADD(9);
       if (warp == 0) {
@@ -2189,7 +1766,8 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
           if (deriv) J.ds[o] = v * prev_tD;  // driver.f90:228
           else {
             J.s[o] = v;
-            if (J.flags) J.flags[o] = flag_prev[zi];
+            if (J.flags) J.flags[o] = flag_prev[zi] != 0ull ? 1 : 0;
+            if (J.smask) J.smask[o] = flag_prev[zi];
           }
         }
         __syncwarp();
@@ -2356,7 +1934,7 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       stale = finish8(&areas[0][0], nacc, T.lt[pi], pvalid ? tot + (size_t)pi * ZB + hl : nullptr, nullptr);
 #endif
 #pragma unroll
-      for (int k = 0; k < ZL; ++k) if (pvalid && (stale & (1 << k))) atomicOr(&flag_cur[GL * k + hl], 1);
+      for (int k = 0; k < ZL; ++k) if (pvalid && (stale & (1 << k))) atomicOr(&flag_cur[GL * k + hl], 1ull << pi);
       PROF_ADD(4);
     }
     PROF_ADD(5);
