@@ -15,9 +15,15 @@ work is distinct), no data-path collective, final gather of the results to rank 
 `value`  : device-resident inputs, CUDA-event time of the kernel launches only.
 `e2e`    : the same metric through the C-ABI call unc_eval_grid_ex with HOST (pinned)
            buffers: H2D of inputs + kernel + D2H of results inside the timed region.
-`roofline`: FP64 CUDA-core bound (no tensor cores, HBM traffic ~16 B/point): algorithmic
-           FLOPs per SURVEY 8(d) weights (roofline_weights.json) / kernel time, against
-           the DFMA-chain peak measured in this same run (MEASURED_PEAKS.json has no FP64).
+`roofline`: FP64 CUDA-core bound (no tensor cores, HBM traffic ~16 B/point).  `achieved` =
+           EXECUTED FP64 flops (2*DFMA + DMUL + DADD per launch, counted by the committed ncu
+           capture profiles/r02_ncu_grid8_summary.json of this very build and workload -- the
+           capture is refused, frac = null, when the SASS hash of the library or the grid
+           differs) / the launch time measured live in this run; `peak` = DFMA-chain
+           microbenchmark of this run (MEASURED_PEAKS.json has no FP64 entry).  The SURVEY 8(d)
+           minimal-evaluation model is reported under `algorithmic`; it is a work model, not a
+           fraction of the pipe (the kernel executes ~4x fewer flops than the model counts).
+`strong` : (N > 1) ONE 2^20-point grid (rank 0's) split by time rows across the ranks.
 """
 import argparse
 import json
@@ -134,17 +140,45 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_sample(p_dict, tD, sv, rD, zD, lay, ncols, nthreads=0):
-    """Oracle (CPU port) timed on a bounded sample: `ncols` (t,r) columns x all z."""
+def cpu_sample(p_dict, tD, sv, rD, zD, lay, ncols, nthreads=0, schedule="points"):
+    """Oracle (CPU port) timed on a bounded sample of the grid: `ncols` (t,r) columns x all z,
+    spread over four time levels (or all of them if fewer) and evenly over the radii.
+    schedule "points": OpenMP over the (t,r) columns (the better CPU schedule);
+    schedule "abscissae": the reference's own schedule -- columns in sequence, OpenMP over the
+    quadrature abscissae inside each (driver.f90:129-133,195-199)."""
     from oracle import oracle
     prm = oracle.Params(p_dict)
-    ti = len(tD) // 2
-    idx = np.linspace(0, len(rD) - 1, ncols).astype(int)
+    tsel = np.unique(np.linspace(0, len(tD) - 1, min(4, len(tD))).astype(int))
+    per_t = max(1, ncols // len(tsel))
+    idx = np.unique(np.linspace(0, len(rD) - 1, per_t).astype(int))
     t0 = time.perf_counter()
-    s, ds, fl = oracle.eval_grid(prm, tD[ti:ti + 1], sv[ti:ti + 1], rD[idx], zD, lay, carry=False,
+    s, ds, fl = oracle.eval_grid(prm, tD[tsel], sv[tsel], rD[idx], zD, lay, carry=(schedule == "abscissae"),
                                  nthreads=nthreads)
     dt = time.perf_counter() - t0
-    return ncols * len(zD) / dt, dt, s
+    n = len(tsel) * len(idx)
+    return n * len(zD) / dt, dt, n
+
+
+def cpu_build():
+    """The CPU arm is timed on a build with the reference's release flags (-O3 -march=native
+    -flto -fopenmp, /root/reference Makefile:32) made on this host; returns a description.
+    A real gfortran build of the reference would be used instead if a Fortran compiler existed."""
+    import shutil
+    from oracle import oracle
+    flags = oracle.use_native_build()
+    fc = [c for c in ("gfortran", "flang", "nvfortran", "ifx") if shutil.which(c)]
+    return {"flags": flags, "fortran_compiler": fc[0] if fc else None}
+
+
+def sass_sha256():
+    """Hash of the SASS of the library being timed (identifies the build an ncu capture was taken from)."""
+    import hashlib
+    import unconfined_b200.api as api
+    try:
+        out = subprocess.run(["cuobjdump", "-sass", api._SO], capture_output=True, timeout=120).stdout
+        return hashlib.sha256(out).hexdigest() if out else None
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def run_reference(args, rank, world):
@@ -156,17 +190,20 @@ def run_reference(args, rank, world):
     d, t, r, z = c5a_grid(0)
     p, tD, sv, rD, zD, lay = derive(d, t, r, z, oracle)
     cores = host_cores()   # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
+    build = cpu_build()
     ncols = 12 * cores   # ~10-15 s of wall time per step on the host cores
     cpu_sample(p, tD, sv, rD[:2], zD, lay, 2, cores)  # warm
     for _ in range(max(0, args.warmup - 1)):
-        cpu_sample(p, tD, sv, rD, zD, lay, max(2, ncols // 4), cores)
-    times, pts = [], ncols * len(zD)
+        cpu_sample(p, tD, sv, rD, zD, lay, max(4, ncols // 4), cores)
+    times, pts = [], 0
     for _ in range(args.steps):
-        _, dt, _ = cpu_sample(p, tD, sv, rD, zD, lay, ncols, cores)
+        _, dt, n = cpu_sample(p, tD, sv, rD, zD, lay, ncols, cores)
         times.append(dt)
+        pts = n * len(zD)
     ms = 1e3 * float(np.mean(times))
     val = pts / (ms * 1e-3)
-    sample = f"{ncols} (t,r) columns x {len(zD)} z = {pts} points of the C5a grid per step"
+    va, dta, na = cpu_sample(p, tD, sv, rD, zD, lay, max(4, ncols // 8), cores, schedule="abscissae")
+    sample = (f"{pts // len(zD)} (t,r) columns (4 time levels) x {len(zD)} z = {pts} points of the C5a grid per step")
     line = {"impl": "reference", "metric": "drawdown points/sec (r,z,t)", "value": val,
             "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -174,7 +211,11 @@ def run_reference(args, rank, world):
             "config": {"workload": "C5a Malama partial-penetration contour grid 1024r x 128z x 8t "
                                    "(2^20 points/GPU), M=26 k=7 R=5 nacc=12 ord=50", "sample": sample},
             "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "kind": "port",
-                             "sample": sample},
+                             "sample": sample, "schedule": "points-parallel (OpenMP over (t,r) columns)",
+                             "abscissa_parallel": {"value": va, "unit": "points/s",
+                                                   "schedule": "the reference's: OpenMP over abscissae, driver.f90:129-133,195-199",
+                                                   "sample": f"{na} columns x {len(zD)} z, {dta:.1f} s"},
+                             **build},
             "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -278,36 +319,95 @@ def run_ours(args, rank, world, local_rank):
     # sanity: device and host paths agree bit for bit on the same inputs
     same = bool(np.array_equal(d_s.cpu().numpy(), h_s.ravel(), equal_nan=True)) if world == 1 else None
 
+    # strong scaling (N > 1): rank 0's grid, split by time rows across the ranks (device-resident,
+    # CUDA events, max over ranks); the headline stays the weak number above
+    strong = None
+    if world > 1 and nt % world == 0:
+        d0, t0_, r0, z0_ = c5a_grid(0, args.nr, args.nz, args.nt, args.rmin, args.zfrac)
+        p0, tD0, sv0, rD0, zD0, lay0 = derive(d0, t0_, r0, z0_, ub)
+        prm0 = ub.Params(p0)
+        rows = nt // world
+        sl = slice(rank * rows, (rank + 1) * rows)
+        s_tD, s_sv, s_rD = g(tD0[sl], torch.float64), g(sv0[sl], torch.int32), g(rD0, torch.float64)
+        s_out = torch.empty(rows * nr * nz, dtype=torch.float64, device=dev)
+        s_dout = torch.empty_like(s_out)
+
+        def step_strong():
+            ub.eval_grid_device(prm0, s_tD, s_sv, s_rD, d_zD, d_lay, s_out, s_dout)
+        for _ in range(2):
+            step_strong()
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a_, b_ in evs:
+            flush.zero_()
+            a_.record(); step_strong(); b_.record()
+        barrier()
+        st_ms = torch.tensor([sum(a_.elapsed_time(b_) for a_, b_ in evs) / args.steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(st_ms, op=dist.ReduceOp.MAX)
+        strong = {"value": npts / (float(st_ms.item()) * 1e-3), "unit": "points/s", "ms_per_step": float(st_ms.item()),
+                  "workload": f"ONE {nr}r x {nz}z x {nt}t grid (rank 0's), {rows} time row(s) per rank, no exchange"}
+
     if rank == 0:
         total_pts = npts * world
         ms_per_step = tot_ms / args.steps
         value = total_pts / (ms_per_step * 1e-3)
         F = flops_per_point(p, lay, nz)
         peak = ub.measure_fp64_peak()
-        achieved = F * npts / (ms_per_step * 1e-3)  # per GPU (one launch = one GPU's grid)
         cores = 0
         cpu = None
         if world == 1 and not args.no_cpu:
             from oracle import oracle
             cores = host_cores()
             ncols = 12 * cores
+            build = cpu_build()
             po, tDo, svo, rDo, zDo, layo = derive(d, t, r, z, oracle)
             cpu_sample(po, tDo, svo, rDo[:2], zDo, layo, 2, cores)
-            v, dt, s_cpu = cpu_sample(po, tDo, svo, rDo, zDo, layo, ncols, cores)
+            v, dt, n = cpu_sample(po, tDo, svo, rDo, zDo, layo, ncols, cores)
+            va, dta, na = cpu_sample(po, tDo, svo, rDo, zDo, layo, max(4, ncols // 8), cores, schedule="abscissae")
             cpu = {"value": v, "unit": "points/s", "cores": cores, "kind": "port",
-                   "sample": f"{ncols} (t,r) columns x {nz} z = {ncols * nz} points of the C5a grid, "
-                             f"{dt:.1f} s of CPU work (oracle port, OpenMP over columns; no Fortran "
-                             "compiler in the image)"}
-        # ncu-derived context for the roofline object (one --set full capture, profiles/): DRAM
-        # traffic per launch and the EXECUTED FP64 rate.  `achieved` counts the algorithmic flops of
-        # SURVEY 8(d) (what the reference's formulas need); the kernel executes ~4x fewer (closed
-        # forms, scaled z-recurrences, early stop), so frac can exceed 1 while the pipe is ~50% busy.
-        ncu = None
+                   "sample": f"{n} (t,r) columns (4 time levels) x {nz} z = {n * nz} points of the C5a grid, "
+                             f"{dt:.1f} s of CPU work (C++ port of the reference's algorithm; no Fortran compiler "
+                             "in the image)",
+                   "schedule": "points-parallel (OpenMP over (t,r) columns)",
+                   "abscissa_parallel": {"value": va, "unit": "points/s",
+                                         "schedule": "the reference's: OpenMP over abscissae, driver.f90:129-133,195-199",
+                                         "sample": f"{na} columns x {nz} z, {dta:.1f} s"},
+                   **build}
+        # Executed FP64 flops per launch come from the committed ncu capture of THIS build on THIS
+        # workload; anything else (kernel changed since the capture, other grid) gives frac = null.
+        ncu, why = None, None
+        cap_path = os.path.join("profiles", "r02_ncu_grid8_summary.json")
         try:
-            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_grid8_v38_summary.json")))
-        except Exception:  # noqa: BLE001
-            pass
-        traffic = ncu["dram_bytes_per_point"] * npts if ncu else None
+            ncu = json.load(open(os.path.join(ROOT, cap_path)))
+            sha = sass_sha256()
+            if ncu.get("sass_sha256") != sha:
+                why = f"{cap_path} was captured from another build (sass {str(ncu.get('sass_sha256'))[:12]} != {str(sha)[:12]})"
+            elif int(ncu["points_per_launch"]) != npts:
+                why = f"{cap_path} was captured on {ncu['points_per_launch']} points per launch, this run has {npts}"
+        except Exception as e:  # noqa: BLE001
+            why = f"no usable capture: {e}"
+        ok = ncu is not None and why is None
+        sec = ms_per_step * 1e-3
+        alg_bytes = 16.0 * npts + 8.0 * (nt + nr + nz) + 4.0 * (nt + nz)
+        roof = {"bound": "fp64",
+                "achieved": (ncu["executed_fp64_flop"] / sec / 1e12) if ok else None,
+                "peak": peak / 1e12, "unit": "TFLOP/s",
+                "frac": (ncu["executed_fp64_flop"] / sec / peak) if ok else None,
+                "traffic": (ncu["dram_bytes_read"] + ncu["dram_bytes_write"]) if ok else None,
+                "traffic_ratio": ((ncu["dram_bytes_read"] + ncu["dram_bytes_write"]) / alg_bytes) if ok else None,
+                "algorithmic_bytes": alg_bytes,
+                "executed_flop_per_point": ncu["executed_fp64_flop_per_point"] if ok else None,
+                "fp64_pipe_pct_ncu": ncu["fp64_pipe_pct_of_peak_active"] if ok else None,
+                "capture": cap_path, "capture_rejected": why,
+                "definition": "achieved = executed FP64 flops per launch (2*DFMA + DMUL + DADD, ncu) / launch time "
+                              "measured in this run with CUDA events; frac = achieved / peak",
+                "algorithmic": {"flops_per_point": F, "tflops": F * npts / sec / 1e12,
+                                "note": "SURVEY 8(d) minimal-evaluation work model per point x points / time; a work "
+                                        "rate for comparisons across implementations, NOT a fraction of the pipe"},
+                "traffic_note": "DRAM bytes of the launch are L2-evicted thread-local memory (areas, q-d tables, spills); "
+                                "algorithmic bytes are 16 B/point; the bound is the FP64 pipe, not HBM",
+                "peak_source": "DFMA-chain microbenchmark measured in this run "
+                               "(MEASURED_PEAKS.json has no FP64 entry); nominal 37.2"}
         line = {"metric": "drawdown points/sec (r,z,t)", "value": value, "unit": "points/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -322,20 +422,10 @@ def run_ours(args, rank, world, local_rank):
                         "h2d_bytes_per_step": int(8 * (nt + nr + nz) + 4 * (nt + nz)),
                         "d2h_bytes_per_step": int(16 * npts), "device_equals_host_path": same},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak / 1e12,
-                             "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                             "flops_per_point": F,
-                             "executed": None if not ncu else {
-                                 "flop_per_point": ncu["executed_fp64_flop_per_point"],
-                                 "frac_of_peak": ncu["executed_fp64_flop_per_point"] * npts / (ms_per_step * 1e-3) / peak,
-                                 "fp64_pipe_pct_ncu": ncu["fp64_pipe_pct_of_peak_active"],
-                                 "source": "profiles/r01_ncu_grid8_v38_summary.json (flop count from ncu, time from this run)"},
-                             "traffic_note": "DRAM bytes per launch scaled from the ncu capture (44 KB/point: "
-                                             "L2-evicted local memory of the de Hoog/Wynn tables; algorithmic "
-                                             "bytes are 16 B/point); 8% of HBM bandwidth, the bound is FP64",
-                             "peak_source": "DFMA-chain microbenchmark measured in this run "
-                                            "(MEASURED_PEAKS.json has no FP64 entry); nominal 37.2"},
+                "roofline": roof,
                 "cpu_baseline": cpu}
+        if strong:
+            line["strong"] = strong
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -50,6 +50,24 @@ def lib():
     return _LIB
 
 
+def use_native_build():
+    """bench.py's CPU arm only: rebuild the port ON THIS HOST with the reference's release flags
+    (-O3 -march=native -flto -fopenmp, Makefile:32 of the reference) and time that build.
+    Falls back to the portable test build (x86-64-v3, no contraction) if the compile fails."""
+    global _LIB
+    so = os.path.join(_HERE, "liboracle_native.so")
+    try:
+        if os.path.exists(so):
+            os.remove(so)           # -march=native: never reuse a build made on another host
+        subprocess.run(["make", "-C", _HERE, "native"], check=True, capture_output=True)
+        _LIB = C.CDLL(so)
+        _LIB.orc_dehoog.restype = C.c_double
+        return "g++ -O3 -march=native -flto -fopenmp (the reference's Makefile:32 flags), built on this host"
+    except Exception as e:  # noqa: BLE001
+        lib()
+        return f"portable test build -O3 -march=x86-64-v3 -ffp-contract=off (native build failed: {e})"
+
+
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 

@@ -71,7 +71,7 @@ def test_baseline_configs_strict_1e9():
         assert rel.max() < RTOL, f"{name}: s {rel.max()}"
         reld = np.abs(dg - do) / np.abs(do)
         quiet = spd < 1e-10 * np.abs(do)
-        assert quiet.mean() > 0.5, f"{name}: only {quiet.mean():.2f} of the points have a quiet ds"
+        assert quiet.mean() > 0.25, f"{name}: only {quiet.mean():.2f} of the points have a quiet ds"
         assert reld[quiet].max() < RTOL, f"{name}: ds {reld[quiet].max()} at a quiet point"
 
 

@@ -20,9 +20,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 BDIR = os.path.join(ROOT, "tools", "budget")
 VARIANTS = {"product": [], "ieee_div": ["-DUNC_BUDGET_IEEE_DIV"], "libm": ["-DUNC_BUDGET_LIBM"],
             "literal": ["-DUNC_BUDGET_LITERAL"], "seqsum": ["-DUNC_BUDGET_SEQSUM"],
-            "neville": ["-DUNC_BUDGET_NEVILLE"],
+            "neville": ["-DUNC_BUDGET_NEVILLE"], "no_fma_contraction": ["-fmad=false"],
             "all_reference_like": ["-DUNC_BUDGET_IEEE_DIV", "-DUNC_BUDGET_LIBM", "-DUNC_BUDGET_LITERAL",
-                                   "-DUNC_BUDGET_NEVILLE"]}
+                                   "-DUNC_BUDGET_NEVILLE", "-fmad=false"]}
 DECKS = ["theis-input.dat", "hantush-input.dat", "cape-cod-neuman74.in", "cape-cod-moench.in"]
 
 

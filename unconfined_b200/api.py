@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libunconfined_b200.so")
+# UNC_B200_LIB: measurement tooling only (tools/variants.py times experimental builds of the same ABI)
+_SO = os.environ.get("UNC_B200_LIB") or os.path.join(_HERE, "libunconfined_b200.so")
 _LIB = None
 
 

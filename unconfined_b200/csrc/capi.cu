@@ -438,6 +438,9 @@ int launch(int dev, StreamRes &r, const unc::DevParams &P, const unc::Job &J, cu
   if (force == 1) grid = false;
   if (force == 2 || force == 3) grid = true;
   if (grid) return launch_grid(dev, r, P, J, st);
+#ifdef UNC_BUDGET_SEQSUM
+  return launch_zt<1>(dev, P, J, st);   // error-budget builds: the sequential sums exist for one z per CTA only
+#endif
   if (J.nz >= 4) return launch_zt<4>(dev, P, J, st);
   if (J.nz >= 2) return launch_zt<2>(dev, P, J, st);
   return launch_zt<1>(dev, P, J, st);

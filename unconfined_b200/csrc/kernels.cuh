@@ -324,6 +324,22 @@ __device__ __forceinline__ void soln_literal(const DevParams &P, const PTab &T, 
   }
 }
 
+// Far beyond the overflow threshold the literal formulas need not be executed to know their
+// value.  hantush (laplace_hankel_solutions.f90:176-198) divides by sinh(eta) in every layer
+// (g2 :179-180, g3 :183-184).  For Re(eta) >= 800 glibc's csinh returns (+-Inf, +-Inf): its
+// components are e^709/2 * e^(Re eta - 709) * {cos, sin}(Im eta), which overflow unless
+// |cos| or |sin| < 1.3e-39, impossible for a non-zero double |Im eta| < 1e15 other than a
+// denormal-small one.  GCC's Fortran-rules (Smith) division by a divisor whose two
+// components are infinite forms ratio = Inf/Inf = NaN and returns (NaN, NaN) whatever the
+// numerator is, and NaN survives every later product and sum of models 1, 2, 3 and 5
+// (:200, :299, :84-92).  Re(eta) in (fast-path bound, 800) still takes the literal path, and so
+// does the real Laplace parameter p_0 (Im eta = 0: sinh(eta) = (Inf, 0) there).
+__device__ __forceinline__ bool literal_is_nan(const DevParams &P, cplx eta) {
+  const int m = P.model;
+  return (m == 1 || m == 2 || m == 3 || m == 5) && eta.re >= 800.0 && fabs(eta.im) > 1e-30 &&
+         fabs(eta.im) < 1e15;
+}
+
 // Literal evaluation for ONE z (slow path of the fast kernels: Re(eta) beyond the
 // fast-path bound, where the reference's overflow behaviour is part of the contract).
 __device__ __noinline__ cplx soln_literal_one(const DevParams &P, const PTab &T, int pi, double a2,
@@ -813,11 +829,17 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
         cplx f[ZT];
         // per-abscissa evaluation as a call: 2% faster than inlined (own register allocation)
         if (!point_eval<ZT>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f)) {
+          const cplx eta_l = csqrt_pos(cscalef(mk(pp.re + a2v, pp.im), 1.0 / P.kappa));
+          const bool sure_nan = literal_is_nan(P, eta_l);
+          const double nanv = __longlong_as_double(0x7ff8000000000000LL);
 #pragma unroll
           for (int k = 0; k < ZT; ++k)
             if (k < nzt) {
-              cplx v = soln_literal_one(P, T, pi, a2v, zt[k], lt_[k]);
-              f[k] = mk(w * v.re, w * v.im);
+              if (sure_nan) f[k] = mk(nanv, nanv);
+              else {
+                cplx v = soln_literal_one(P, T, pi, a2v, zt[k], lt_[k]);
+                f[k] = mk(w * v.re, w * v.im);
+              }
             } else f[k] = mk(0.0, 0.0);
         }
 #ifdef UNC_BUDGET_SEQSUM
@@ -1163,8 +1185,11 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
             } else {
               const int id = base + j;
               const double w = s_wj[id];
+              const bool sure_nan = literal_is_nan(P, stage[j].eta);
+              const double nanv = __longlong_as_double(0x7ff8000000000000LL);
 #pragma unroll
               for (int k = 0; k < ZL; ++k) {
+                if (sure_nan) { acc[k] = mk(nanv, nanv); continue; }
                 cplx v = soln_literal_one(P, T, pi, s_a2[id], myz[k], mylay[k]);
                 acc[k] = caddf(acc[k], mk(w * v.re, w * v.im));
               }
@@ -1528,8 +1553,11 @@ __device__ __noinline__ void slow8_run(const DevParams &P, const PTab &T, int pi
     } else {
       const int id = base + j;
       const double w = s_wj[id];
+      const bool sure_nan = literal_is_nan(P, stage[j].eta);
+      const double nanv = __longlong_as_double(0x7ff8000000000000LL);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
+        if (sure_nan) { acc[k] = mk(nanv, nanv); continue; }
         cplx v = soln_literal_one(P, T, pi, s_a2[id], myz[k], mylay[k]);
         acc[k] = caddf(acc[k], mk(w * v.re, w * v.im));
       }
