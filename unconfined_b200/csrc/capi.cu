@@ -337,25 +337,45 @@ int upload_tables(StreamRes &r, HostPlan &hp, cudaStream_t st) {
   return UNC_OK;
 }
 
-template <int ZT>
-int launch_zt(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st, long long nblk_fix = -1) {
+template <int ZT, int PT>
+int launch_point(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st, long long nunits) {
   const int na = P.nts_pad + P.gl_rounds * 32;
-  const size_t smem = unc::smem_bytes(P.np, P.nacc, na, ZT);
+  const size_t smem = unc::point_smem_bytes(P.np, P.nacc, na, ZT, PT);
   if (smem > 227 * 1024) return fail(UNC_ERR_UNSUPPORTED, "shared memory need %zu B exceeds 227 KB", smem);
   DevCtx &c = g_ctx[dev];
-  if (!c.smem_set[ZT]) {
-    CK(cudaFuncSetAttribute(unc::lh_point_kernel<ZT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (!c.smem_set[ZT + 4 * (PT - 1)]) {
+    CK(cudaFuncSetAttribute(unc::lh_point_kernel<ZT, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             227 * 1024));
-    c.smem_set[ZT] = true;
+    c.smem_set[ZT + 4 * (PT - 1)] = true;
   }
-  const long long ntiles = (J.nz + ZT - 1) / ZT;
-  const long long nblk = nblk_fix >= 0 ? nblk_fix : J.ncol * ntiles;
+  const long long nblk = (nunits + PT - 1) / PT;
   if (nblk <= 0) return UNC_OK;
   if (nblk > 2147483647LL) return fail(UNC_ERR_UNSUPPORTED, "too many work items (%lld)", nblk);
-  unc::lh_point_kernel<ZT><<<(unsigned)nblk, UNC_THREADS, smem, st>>>(P, J);
+  unc::lh_point_kernel<ZT, PT><<<(unsigned)nblk, UNC_THREADS, smem, st>>>(P, J);
   g_launches++;
   CK(cudaGetLastError());
   return UNC_OK;
+}
+
+// ZT z-values of one column per work unit; for ZT = 1 (scattered points, time series) a CTA takes
+// up to four units so that its Wynn and de Hoog phases are full -- when there are enough units to
+// fill the GPU that way and two such CTAs still fit an SM
+template <int ZT>
+int launch_zt(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st, long long nunits_fix = -1) {
+  const long long ntiles = (J.nz + ZT - 1) / ZT;
+  const long long nunits = nunits_fix >= 0 ? nunits_fix : J.ncol * ntiles;
+  if (ZT == 1) {
+#ifndef UNC_BUDGET_SEQSUM
+    const int na = P.nts_pad + P.gl_rounds * 32;
+    const long long fill = 2LL * g_ctx[dev].sm_count;
+    if (nunits >= 4 * fill && 2 * unc::point_smem_bytes(P.np, P.nacc, na, 1, 4) <= 227 * 1024)
+      return launch_point<1, 4>(dev, P, J, st, nunits);
+    if (nunits >= 2 * fill && 2 * unc::point_smem_bytes(P.np, P.nacc, na, 1, 2) <= 227 * 1024)
+      return launch_point<1, 2>(dev, P, J, st, nunits);
+#endif
+    return launch_point<1, 1>(dev, P, J, st, nunits);
+  }
+  return launch_point<ZT, 1>(dev, P, J, st, nunits);
 }
 
 template <int ZL>
@@ -498,6 +518,7 @@ int carry_postpass(int dev, StreamRes &r, const unc::DevParams &P, unc::Job Jg, 
   unc::Job Js = Jg;
   Js.s = Js.ds = nullptr; Js.flags = nullptr; Js.smask = nullptr;
   Js.fix_mode = 1;
+  Js.fix_n = ns;
   Js.fix_list = (const int *)r.src_list.ptr;
   Js.fix_need = (const unsigned long long *)r.need.ptr;
   Js.fix_val = (double *)r.fix_val.ptr;
@@ -506,6 +527,7 @@ int carry_postpass(int dev, StreamRes &r, const unc::DevParams &P, unc::Job Jg, 
   unc::Job Jd = Jg;
   Jd.flags = nullptr; Jd.smask = nullptr;
   Jd.fix_mode = 2;
+  Jd.fix_n = nf;
   Jd.fix_list = (const int *)r.list.ptr;
   Jd.fix_src = (const int *)r.fix_src.ptr;
   Jd.fix_val = (double *)r.fix_val.ptr;

@@ -328,16 +328,24 @@ __device__ __forceinline__ void soln_literal(const DevParams &P, const PTab &T, 
 // value.  hantush (laplace_hankel_solutions.f90:176-198) divides by sinh(eta) in every layer
 // (g2 :179-180, g3 :183-184).  For Re(eta) >= 800 glibc's csinh returns (+-Inf, +-Inf): its
 // components are e^709/2 * e^(Re eta - 709) * {cos, sin}(Im eta), which overflow unless
-// |cos| or |sin| < 1.3e-39, impossible for a non-zero double |Im eta| < 1e15 other than a
-// denormal-small one.  GCC's Fortran-rules (Smith) division by a divisor whose two
+// |cos| or |sin| < 1.3e-39, impossible for a non-zero double |Im eta| < 2e5 other than a
+// denormal-small one; between 718 and 800 the same is established from the actual sine and
+// cosine (below).  GCC's Fortran-rules (Smith) division by a divisor whose two
 // components are infinite forms ratio = Inf/Inf = NaN and returns (NaN, NaN) whatever the
 // numerator is, and NaN survives every later product and sum of models 1, 2, 3 and 5
-// (:200, :299, :84-92).  Re(eta) in (fast-path bound, 800) still takes the literal path, and so
+// (:200, :299, :84-92).  Re(eta) in (fast-path bound, 718) still takes the literal path, and so
 // does the real Laplace parameter p_0 (Im eta = 0: sinh(eta) = (Inf, 0) there).
 __device__ __forceinline__ bool literal_is_nan(const DevParams &P, cplx eta) {
   const int m = P.model;
-  return (m == 1 || m == 2 || m == 3 || m == 5) && eta.re >= 800.0 && fabs(eta.im) > 1e-30 &&
-         fabs(eta.im) < 1e15;
+  if (!((m == 1 || m == 2 || m == 3 || m == 5) && eta.re >= 718.0 && fabs(eta.im) < 2.0e5)) return false;
+  if (eta.re >= 800.0) return fabs(eta.im) > 1e-30;
+  // closer to the threshold the overflow of BOTH components is checked on the actual phase:
+  // |component| = e^709.78 * e^(Re eta - 709.78)/2 * |cos or sin|, so Re eta >= 718 (e^8.2/2 = 1.8e3)
+  // overflows whenever |cos|, |sin| > 1e-3; Re eta >= 745 (e^35/2 = 8e14) whenever they exceed 1e-10
+  double sn, cs;
+  sincos_q(eta.im, &sn, &cs);
+  const double mn = fmin(fabs(sn), fabs(cs));
+  return mn > 1e-3 || (eta.re >= 745.0 && mn > 1e-10);
 }
 
 // Literal evaluation for ONE z (slow path of the fast kernels: Re(eta) beyond the
@@ -619,23 +627,6 @@ __device__ __noinline__ cplx wynn_grid(const cplx *series, int nacc) {
 __device__ __forceinline__ double shfl_down_d(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ double shfl_xor_d(double v, int d) { return __shfl_xor_sync(0xffffffffu, v, d); }
 
-// shared-memory carve-up (bytes) for a given parameter set
-__host__ __device__ inline size_t smem_bytes(int np, int nacc, int na, int ZT) {
-  size_t b = 0;
-  b += (size_t)4 * np * sizeof(cplx);                 // p, lt, aux, aux2
-  b += (size_t)2 * na * sizeof(double);               // a2, wj
-  size_t areas = (size_t)np * ZT * nacc * sizeof(cplx);
-  size_t scratch = (size_t)UNC_WARPS * 3 * np * sizeof(cplx);  // de Hoog q,e,d per warp (aliases areas)
-  b += areas > scratch ? areas : scratch;
-  b += (size_t)np * ZT * sizeof(cplx);                // finint -> totlap
-  b += (size_t)ZT * (2 * sizeof(double) + sizeof(int));  // z, stale masks (64 bit), lay
-  b = (b + 15) & ~(size_t)15;
-#ifdef UNC_BUDGET_SEQSUM
-  b += (size_t)UNC_WARPS * na * sizeof(cplx);           // every abscissa's value, per warp
-#endif
-  return b;
-}
-
 // Fast-path evaluation of one abscissa for the ZT z-values of a point-kernel tile, as a
 // separate function (own register allocation; the kernel around it holds the accumulators).
 template <int ZT, int MODEL, int LMASK>
@@ -687,74 +678,135 @@ __device__ __forceinline__ bool point_eval(const DevParams &P, cplx pp, cplx aux
 #ifndef UNC_POINT_MINB
 #define UNC_POINT_MINB 2   // 128 registers, 16 warps per SM: C5b 481 ms vs 595 ms at 226 registers and 8 warps
 #endif
-template <int ZT>
+// Work unit = one (t,r) column and a tile of ZT z-values; a CTA takes PT units (PT > 1 only with
+// ZT = 1: scattered points and time series, where the Wynn phase has np and the de Hoog phase
+// two jobs per unit -- a quarter of the threads and of the warps of a CTA; with four units per
+// CTA both phases are full).
+struct PointUnit {
+  long long col;
+  double tD, tee;
+  double eta_max;
+  int z0, nzt, lay_mask, valid;
+};
+
+__host__ __device__ inline size_t point_unit_bytes(int np, int nacc, int na, int ZT) {
+  size_t b = 0;
+  b += (size_t)4 * np * sizeof(cplx);                 // p, lt, aux, aux2
+  b += (size_t)2 * na * sizeof(double);               // a2, wj
+  b += (size_t)np * ZT * sizeof(cplx);                // finint -> totlap
+  b += (size_t)ZT * (2 * sizeof(double) + 2 * sizeof(int));  // z, stale masks (64 bit), lay (padded)
+  return (b + 15) & ~(size_t)15;
+}
+
+__host__ __device__ inline size_t point_smem_bytes(int np, int nacc, int na, int ZT, int PT) {
+  size_t areas = (size_t)PT * np * ZT * nacc * sizeof(cplx);
+  size_t scratch = (size_t)UNC_WARPS * 3 * np * sizeof(cplx);  // de Hoog q,e,d per warp (aliases the areas)
+  size_t b = (areas > scratch ? areas : scratch) + (size_t)PT * point_unit_bytes(np, nacc, na, ZT);
+  b += (size_t)PT * sizeof(PointUnit);
+  b = (b + 15) & ~(size_t)15;
+#ifdef UNC_BUDGET_SEQSUM
+  b += (size_t)UNC_WARPS * na * sizeof(cplx);           // every abscissa's value, per warp
+#endif
+  return b;
+}
+
+template <int ZT, int PT>
 __global__ void __launch_bounds__(UNC_THREADS, UNC_POINT_MINB)
 lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job J) {
+  static_assert(ZT == 1 || PT == 1, "several units per CTA only for one z per unit");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int np = P.np, nacc = P.nacc, G = P.G;
   const int na = P.nts_pad + P.gl_rounds * 32;
   const int ntiles = (J.nz + ZT - 1) / ZT;
-  // carry post-pass (ZT == 1 only): the CTA's point comes from a list instead of the launch grid
+  // carry post-pass (ZT == 1 only): the units come from a list instead of the launch grid
   const int fix_mode = (ZT == 1) ? J.fix_mode : 0;
-  const long long fix_pt = fix_mode ? (long long)J.fix_list[blockIdx.x] : 0;
-  const long long col = fix_mode ? fix_pt / J.nz : blockIdx.x / ntiles;
-  const int tile = fix_mode ? (int)(fix_pt % J.nz) : (int)(blockIdx.x % ntiles);
-  const int z0 = tile * ZT;
-  const int nzt = min(ZT, J.nz - z0);
-  const unsigned long long pmask = (fix_mode == 1) ? J.fix_need[fix_pt] : ~0ull;   // p to evaluate
+  const long long nunits = fix_mode ? J.fix_n : J.ncol * (long long)ntiles;
+  const long long unit0 = (long long)blockIdx.x * PT;
 
-  // carve shared memory
+  // carve shared memory: areas of all units | per-unit tables | unit descriptors
   unsigned char *sp = smem_raw;
-  PTab T;
-  T.p = (cplx *)sp; sp += np * sizeof(cplx);
-  T.lt = (cplx *)sp; sp += np * sizeof(cplx);
-  T.aux = (cplx *)sp; sp += np * sizeof(cplx);
-  T.aux2 = (cplx *)sp; sp += np * sizeof(cplx);
-  double *s_a2 = (double *)sp; sp += na * sizeof(double);
-  double *s_wj = (double *)sp; sp += na * sizeof(double);
-  cplx *s_area = (cplx *)sp;
+  cplx *s_area_all = (cplx *)sp;
   {
-    size_t areas = (size_t)np * ZT * nacc * sizeof(cplx);
+    size_t areas = (size_t)PT * np * ZT * nacc * sizeof(cplx);
     size_t scratch = (size_t)UNC_WARPS * 3 * np * sizeof(cplx);
     sp += areas > scratch ? areas : scratch;
   }
-  cplx *s_fin = (cplx *)sp; sp += (size_t)np * ZT * sizeof(cplx);
-  double *s_z = (double *)sp; sp += ZT * sizeof(double);
-  unsigned long long *s_mask = (unsigned long long *)sp; sp += ZT * sizeof(unsigned long long);
-  int *s_lay = (int *)sp;
+  unsigned char *unit_base = sp;
+  const size_t ub = point_unit_bytes(np, nacc, na, ZT);
+  sp += (size_t)PT * ub;
+  PointUnit *s_unit = (PointUnit *)sp;
 #ifdef UNC_BUDGET_SEQSUM
-  static_assert(ZT >= 1, "");
-  cplx *s_seq = (cplx *)(smem_raw + smem_bytes(np, nacc, na, ZT)) - (size_t)UNC_WARPS * na + (size_t)warp * na;
+  cplx *s_seq = (cplx *)(smem_raw + point_smem_bytes(np, nacc, na, ZT, PT)) - (size_t)UNC_WARPS * na + (size_t)warp * na;
 #endif
-
-  const long long tcol = col + J.col0;
-  const double tD = J.tD[tcol / J.tdiv];
-  const int sv = J.sv[tcol / J.tdiv];
-  const double rD = J.rD[tcol % J.rmod];
-  const double tee = P.tee_mult * tD;
-  const double arg = P.j0z[sv - 1] / rD;                      // driver.f90:120
-  const double tscale = J.ts_scale ? J.ts_scale[col] : arg;  // driver.f90:121-126
-  const double *zsrc = J.zD + (J.zstride ? col * (long long)J.nz : 0) + z0;
-  const int *lsrc = J.zLay + (J.zstride ? col * (long long)J.nz : 0) + z0;
+  struct UnitMem {
+    PTab T;
+    double *a2, *wj;
+    cplx *fin;
+    double *z;
+    unsigned long long *mask;
+    int *lay;
+  };
+  auto unit_mem = [&](int u) {
+    UnitMem m;
+    unsigned char *q = unit_base + (size_t)u * ub;
+    m.T.p = (cplx *)q; q += np * sizeof(cplx);
+    m.T.lt = (cplx *)q; q += np * sizeof(cplx);
+    m.T.aux = (cplx *)q; q += np * sizeof(cplx);
+    m.T.aux2 = (cplx *)q; q += np * sizeof(cplx);
+    m.a2 = (double *)q; q += na * sizeof(double);
+    m.wj = (double *)q; q += na * sizeof(double);
+    m.fin = (cplx *)q; q += (size_t)np * ZT * sizeof(cplx);
+    m.z = (double *)q; q += ZT * sizeof(double);
+    m.mask = (unsigned long long *)q; q += ZT * sizeof(unsigned long long);
+    m.lay = (int *)q;
+    return m;
+  };
 
   // ---- prologue -------------------------------------------------------------
-  if (tid < ZT) {
-    s_z[tid] = (tid < nzt) ? zsrc[tid] : 0.0;
-    s_lay[tid] = (tid < nzt) ? lsrc[tid] : 2;
-    s_mask[tid] = 0ull;
+  if (tid < PT) {
+    const int u = tid;
+    const long long U = unit0 + u;
+    PointUnit d;
+    d.valid = U < nunits ? 1 : 0;
+    const long long pt = d.valid ? (fix_mode ? (long long)J.fix_list[U] : U) : 0;
+    d.col = fix_mode ? pt / J.nz : pt / ntiles;
+    d.z0 = (fix_mode ? (int)(pt % J.nz) : (int)(pt % ntiles)) * ZT;
+    d.nzt = d.valid ? min(ZT, J.nz - d.z0) : 0;
+    const long long tcol = d.col + J.col0;
+    d.tD = J.tD[tcol / J.tdiv];
+    d.tee = P.tee_mult * d.tD;
+    UnitMem m = unit_mem(u);
+    const double *zsrc = J.zD + (J.zstride ? d.col * (long long)J.nz : 0) + d.z0;
+    const int *lsrc = J.zLay + (J.zstride ? d.col * (long long)J.nz : 0) + d.z0;
+    int lay_mask = 0;
+    double zabs = 0.0;
+    for (int i = 0; i < ZT; ++i) {
+      const double zv = (i < d.nzt) ? zsrc[i] : 0.0;
+      const int lv = (i < d.nzt) ? lsrc[i] : 2;
+      m.z[i] = zv; m.lay[i] = lv; m.mask[i] = 0ull;
+      if (i < d.nzt) { lay_mask |= 1 << (lv - 1); zabs = fmax(zabs, fabs(zv)); }
+    }
+    d.lay_mask = lay_mask;
+    d.eta_max = fast_eta_max(P, lay_mask, zabs);
+    s_unit[u] = d;
   }
-  for (int i = tid; i < np; i += UNC_THREADS) {
+  __syncthreads();
+  for (int k = tid; k < PT * np; k += UNC_THREADS) {
+    const int u = k / np, i = k - u * np;
+    if (!s_unit[u].valid) continue;
+    UnitMem m = unit_mem(u);
+    const double tee = s_unit[u].tee;
     // invlap.f90:166-170
     const double PI = 3.141592653589793;
     double sigma = P.alpha - P.log_tol / (2.0 * tee);
     cplx p = mk(sigma, PI * (double)i / tee);
-    T.p[i] = p;
-    T.lt[i] = laptime_dev(P, p);
+    m.T.p[i] = p;
+    m.T.lt[i] = laptime_dev(P, p);
     cplx aux = mk(0.0, 0.0), aux2 = mk(0.0, 0.0);
     if (P.model == 3) {
       // sum(1/(1 + p .X. 1/gamma), dim=2)   laplace_hankel_solutions.f90:74
-      for (int m = 0; m < P.moench_M; ++m) aux = aux + 1.0 / (1.0 + p * (1.0 / P.moench_gamma[m]));
+      for (int mm = 0; mm < P.moench_M; ++mm) aux = aux + 1.0 / (1.0 + p * (1.0 / P.moench_gamma[mm]));
     } else if (P.model == 2) {
       // :253-266  xi = rDw*sqrt(p); A0 = 2/(p*CDw*K0 + xi*K1)
       cplx xi = P.rDw * csqrt_g(p);
@@ -763,10 +815,18 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       aux = 2.0 / (p * P.CDw * K[0] + xi * K[1]);
       aux2 = p * P.tDb + 1.0;
     }
-    T.aux[i] = aux;
-    T.aux2[i] = aux2;
+    m.T.aux[i] = aux;
+    m.T.aux2[i] = aux2;
   }
-  for (int idx = tid; idx < na; idx += UNC_THREADS) {
+  for (int k = tid; k < PT * na; k += UNC_THREADS) {
+    const int u = k / na, idx = k - u * na;
+    if (!s_unit[u].valid) continue;
+    UnitMem m = unit_mem(u);
+    const long long col = s_unit[u].col, tcol = col + J.col0;
+    const int sv = J.sv[tcol / J.tdiv];
+    const double rD = J.rD[tcol % J.rmod];
+    const double arg = P.j0z[sv - 1] / rD;                      // driver.f90:120
+    const double tscale = J.ts_scale ? J.ts_scale[col] : arg;  // driver.f90:121-126
     double a = 0.0, w = 0.0;
     if (idx < P.nts_pad) {
       if (idx < P.N) {
@@ -777,46 +837,46 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
 #endif
       }
     } else {
-      const int k = idx - P.nts_pad;
-      const int L = k & 31, i = k >> 5;
+      const int kk = idx - P.nts_pad;
+      const int L = kk & 31, i = kk >> 5;
       const int node = L * P.gl_rounds + i;
       if (node < nacc * G) {
-        const int j = node / G, m = node - j * G;
+        const int j = node / G, mm = node - j * G;
         const double lob = P.j0z[sv + j - 1] / rD;  // driver.f90:188-193
         const double hib = P.j0z[sv + j] / rD;
         const double width = hib - lob;
-        a = fma(width, P.gl_x[m], hib + lob) / 2.0;
-        w = P.gl_w[m] * (width / 2.0);
+        a = fma(width, P.gl_x[mm], hib + lob) / 2.0;
+        w = P.gl_w[mm] * (width / 2.0);
       }
     }
-    s_a2[idx] = a * a;
-    s_wj[idx] = (w != 0.0) ? w * (a * j0_dev(a * rD)) : 0.0;  // laplace_hankel_solutions.f90:118
+    m.a2[idx] = a * a;
+    m.wj[idx] = (w != 0.0) ? w * (a * j0_dev(a * rD)) : 0.0;  // laplace_hankel_solutions.f90:118
   }
   __syncthreads();
 
-  // ---- phase A: Hankel quadrature sums, one warp per p ------------------------
+  // ---- phase A: Hankel quadrature sums, one warp per (unit, p) ------------------
   const int rounds = P.gl_rounds;
   const int node0 = lane * rounds;
   const int jA = node0 / G;
   const int iB = (jA + 1) * G - node0;  // first round that falls in interval jA+1
   const int jA_valid = (node0 < nacc * G) ? jA : -1 - lane;  // distinct ids for empty lanes
-  double zt[ZT];
-  int lt_[ZT];
-#pragma unroll
-  for (int i = 0; i < ZT; ++i) { zt[i] = s_z[i]; lt_[i] = s_lay[i]; }
-
-  int lay_mask = 0;
-  double zabs = 0.0;
-#pragma unroll
-  for (int i = 0; i < ZT; ++i) if (i < nzt) { lay_mask |= 1 << (lt_[i] - 1); zabs = fmax(zabs, fabs(zt[i])); }
-  const double eta_max = fast_eta_max(P, lay_mask, zabs);
-
-  for (int pi = warp; pi < np; pi += UNC_WARPS) {
+  for (int job = warp; job < PT * np; job += UNC_WARPS) {
+    const int u = job / np, pi = job - u * np;
+    const PointUnit un = s_unit[u];
+    if (!un.valid) continue;
+    const UnitMem m = unit_mem(u);
+    const unsigned long long pmask = (fix_mode == 1) ? J.fix_need[J.fix_list[unit0 + u]] : ~0ull;   // p to evaluate
     if (!((pmask >> pi) & 1ull)) continue;
+    const int nzt = un.nzt, lay_mask = un.lay_mask;
+    const double eta_max = un.eta_max;
+    double zt[ZT];
+    int lt_[ZT];
+#pragma unroll
+    for (int i = 0; i < ZT; ++i) { zt[i] = m.z[i]; lt_[i] = m.lay[i]; }
     cplx accT[ZT], accA[ZT], accB[ZT];
 #pragma unroll
     for (int i = 0; i < ZT; ++i) { accT[i] = mk(0, 0); accA[i] = mk(0, 0); accB[i] = mk(0, 0); }
-    const cplx pp = T.p[pi], aux = T.aux[pi], aux2 = T.aux2[pi];
+    const cplx pp = m.T.p[pi], aux = m.T.aux[pi], aux2 = m.T.aux2[pi];
     const int nts_rounds = P.nts_pad / 32;
     // one abscissa per lane per round: tanh-sinh rounds first, then Gauss-Lobatto rounds
     // (a source of the carry post-pass only needs the Gauss-Lobatto part)
@@ -825,7 +885,7 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       const int idx = ts ? i * 32 + lane : P.nts_pad + (i - nts_rounds) * 32 + lane;
       const bool valid = ts ? (idx < P.N) : (node0 + (i - nts_rounds) < nacc * G);
       if (valid) {
-        const double w = s_wj[idx], a2v = s_a2[idx];
+        const double w = m.wj[idx], a2v = m.a2[idx];
         cplx f[ZT];
         // per-abscissa evaluation as a call: 2% faster than inlined (own register allocation)
         if (!point_eval<ZT>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f)) {
@@ -837,7 +897,7 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
             if (k < nzt) {
               if (sure_nan) f[k] = mk(nanv, nanv);
               else {
-                cplx v = soln_literal_one(P, T, pi, a2v, zt[k], lt_[k]);
+                cplx v = soln_literal_one(P, m.T, pi, a2v, zt[k], lt_[k]);
                 f[k] = mk(w * v.re, w * v.im);
               }
             } else f[k] = mk(0.0, 0.0);
@@ -858,13 +918,13 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       }
     }
     // reductions
-    cplx *area_p = s_area + (size_t)pi * ZT * nacc;
+    cplx *area_p = s_area_all + ((size_t)u * np + pi) * ZT * nacc;
     for (int k = lane; k < ZT * nacc; k += 32) area_p[k] = mk(0.0, 0.0);
 #pragma unroll
     for (int k = 0; k < ZT; ++k) {
       double tr = accT[k].re, ti = accT[k].im;
       for (int o = 16; o > 0; o >>= 1) { tr += shfl_xor_d(tr, o); ti += shfl_xor_d(ti, o); }
-      if (lane == 0) s_fin[pi * ZT + k] = mk(tr, ti);
+      if (lane == 0) m.fin[pi * ZT + k] = mk(tr, ti);
       double ar = accA[k].re, ai = accA[k].im;
       for (int dlt = 1; dlt < 32; dlt <<= 1) {
         double orr = shfl_down_d(ar, dlt), oi = shfl_down_d(ai, dlt);
@@ -895,7 +955,7 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       for (int j = 1; j <= R; ++j) {
         const int kv = P.ts_k - R + j, Nv = (1 << kv) - 1, step = 1 << (R - j);
         cplx sum = mk(0.0, 0.0);
-        for (int m = 1; m <= Nv; ++m) sum = caddf(sum, cscalef(s_seq[m * step - 1], lw[m - 1]));
+        for (int mm = 1; mm <= Nv; ++mm) sum = caddf(sum, cscalef(s_seq[mm * step - 1], lw[mm - 1]));
         lw += Nv;
         c_[j - 1] = d_[j - 1] = sum;
         x_[j - 1] = 4.0 / (double)(1 << kv);
@@ -903,27 +963,27 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       int ns = R;                    // hv decreasing: the smallest x is the last
       cplx y = c_[ns - 1];
       ns -= 1;
-      for (int m = 1; m <= R - 1; ++m) {
-        for (int i = 1; i <= R - m; ++i) {
-          const double dx = x_[i - 1] - x_[i + m - 1];
+      for (int mm = 1; mm <= R - 1; ++mm) {
+        for (int i = 1; i <= R - mm; ++i) {
+          const double dx = x_[i - 1] - x_[i + mm - 1];
           const cplx den = mk((c_[i].re - d_[i - 1].re) / dx, (c_[i].im - d_[i - 1].im) / dx);
-          d_[i - 1] = cscalef(den, x_[i + m - 1]);
+          d_[i - 1] = cscalef(den, x_[i + mm - 1]);
           c_[i - 1] = cscalef(den, x_[i - 1]);
         }
         cplx dy;
-        if (2 * ns < R - m) dy = c_[ns];
+        if (2 * ns < R - mm) dy = c_[ns];
         else { dy = d_[ns - 1]; ns -= 1; }
         y = caddf(y, dy);
       }
-      s_fin[pi * ZT] = (R > 1) ? y : c_[0];
+      m.fin[pi * ZT] = (R > 1) ? y : c_[0];
 #else
       cplx sum = mk(0.0, 0.0);
-      for (int m = 0; m < P.N; ++m) sum = caddf(sum, s_seq[m]);
-      s_fin[pi * ZT] = sum;
+      for (int mm = 0; mm < P.N; ++mm) sum = caddf(sum, s_seq[mm]);
+      m.fin[pi * ZT] = sum;
 #endif
       for (int j = 0; j < nacc; ++j) {
         cplx a_ = mk(0.0, 0.0);
-        for (int m = 0; m < G; ++m) a_ = caddf(a_, s_seq[P.N + j * G + m]);
+        for (int mm = 0; mm < G; ++mm) a_ = caddf(a_, s_seq[P.N + j * G + mm]);
         area_p[j] = a_;
       }
     }
@@ -932,16 +992,20 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
   }
   __syncthreads();
 
-  // ---- phase B: Wynn-epsilon per (p,z), totlap = finint + infint ---------------
-  for (int k = tid; k < np * ZT; k += UNC_THREADS) {
-    const int pi = k / ZT, zi = k - pi * ZT;
-    if (zi < nzt && ((pmask >> pi) & 1ull)) {
+  // ---- phase B: Wynn-epsilon per (unit,p,z), totlap = finint + infint -----------
+  for (int k = tid; k < PT * np * ZT; k += UNC_THREADS) {
+    const int u = k / (np * ZT), kk = k - u * (np * ZT);
+    const int pi = kk / ZT, zi = kk - pi * ZT;
+    if (!s_unit[u].valid) continue;
+    const UnitMem m = unit_mem(u);
+    const unsigned long long pmask = (fix_mode == 1) ? J.fix_need[J.fix_list[unit0 + u]] : ~0ull;
+    if (zi < s_unit[u].nzt && ((pmask >> pi) & 1ull)) {
       const double nan = __longlong_as_double(0x7ff8000000000000LL);
-      const cplx lt = T.lt[pi];
+      const cplx lt = m.T.lt[pi];
       cplx series[UNC_MAX_NACC];
       bool any = false;
       for (int j = 0; j < nacc; ++j) {
-        cplx a = s_area[((size_t)pi * ZT + zi) * nacc + j];
+        cplx a = s_area_all[(((size_t)u * np + pi) * ZT + zi) * nacc + j];
         a = is_finite_c(a) ? a * lt : mk(nan, nan);
         series[j] = a;
         if (cabs_d(a) > 0.0) any = true;   // driver.f90:209
@@ -949,10 +1013,10 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       cplx infint = mk(0.0, 0.0);
       if (any) infint = wynn_any(series, nacc);
       else {
-        atomicOr(&s_mask[zi], 1ull << pi);
+        atomicOr(&m.mask[zi], 1ull << pi);
         if (fix_mode == 2) {
           // driver.f90:209-211: infint(p,z) keeps the value of the last (t,r) that set it
-          const int src = J.fix_src[(size_t)blockIdx.x * np + pi];
+          const int src = J.fix_src[(size_t)(unit0 + u) * np + pi];
           if (src >= 0) {
             const double *v = J.fix_val + ((size_t)src * np + pi) * 2;
             infint = mk(v[0], v[1]);
@@ -960,33 +1024,38 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
         }
       }
       if (fix_mode == 1) {
-        double *v = J.fix_val + ((size_t)blockIdx.x * np + pi) * 2;
+        double *v = J.fix_val + ((size_t)(unit0 + u) * np + pi) * 2;
         v[0] = infint.re; v[1] = infint.im;
       }
-      cplx fin = s_fin[k];
+      cplx fin = m.fin[kk];
       fin = is_finite_c(fin) ? fin * lt : mk(nan, nan);
-      s_fin[k] = fin + infint;  // totlap, driver.f90:216
+      m.fin[kk] = fin + infint;  // totlap, driver.f90:216
     }
   }
   __syncthreads();
   if (fix_mode == 1) return;
 
   // ---- phase C: de Hoog inversion of value and log-time derivative ------------
-  cplx *scr = s_area + (size_t)warp * 3 * np;
-  for (int job = warp; job < 2 * nzt; job += UNC_WARPS) {
-    const int zi = job >> 1, deriv = job & 1;
-    double v = dehoog_warp(P, s_fin + zi, ZT, deriv ? T.p : nullptr, tD, tee, scr, scr + np,
+  cplx *scr = s_area_all + (size_t)warp * 3 * np;
+  for (int job = warp; job < PT * 2 * ZT; job += UNC_WARPS) {
+    const int u = job / (2 * ZT), jj = job - u * (2 * ZT);
+    const int zi = jj >> 1, deriv = jj & 1;
+    const PointUnit un = s_unit[u];
+    if (!un.valid || zi >= un.nzt) continue;
+    const UnitMem m = unit_mem(u);
+    double v = dehoog_warp(P, m.fin + zi, ZT, deriv ? m.T.p : nullptr, un.tD, un.tee, scr, scr + np,
                            scr + 2 * np, lane);
     if (lane == 0) {
-      const long long o = col * (long long)J.nz + z0 + zi;
+      const long long o = un.col * (long long)J.nz + un.z0 + zi;
+      const long long U = unit0 + u;
       if (fix_mode == 2) {
-        if (deriv) { J.fix_ds[blockIdx.x] = v * tD; if (J.ds) J.ds[o] = v * tD; }
-        else { J.fix_s[blockIdx.x] = v; if (J.s) J.s[o] = v; }
-      } else if (deriv) J.ds[o] = v * tD;  // driver.f90:228
+        if (deriv) { J.fix_ds[U] = v * un.tD; if (J.ds) J.ds[o] = v * un.tD; }
+        else { J.fix_s[U] = v; if (J.s) J.s[o] = v; }
+      } else if (deriv) J.ds[o] = v * un.tD;  // driver.f90:228
       else {
         J.s[o] = v;
-        if (J.flags) J.flags[o] = s_mask[zi] != 0ull ? 1 : 0;
-        if (J.smask) J.smask[o] = s_mask[zi];
+        if (J.flags) J.flags[o] = m.mask[zi] != 0ull ? 1 : 0;
+        if (J.smask) J.smask[o] = m.mask[zi];
       }
     }
     __syncwarp();

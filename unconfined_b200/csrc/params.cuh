@@ -45,6 +45,7 @@ struct Job {
   // carry post-pass (lh_point_kernel<1> only; capi.cu carry_postpass): CTA e works on point fix_list[e]
   int fix_mode;               // 0 normal; 1 source: Wynn result of the p in need[] -> fix_val;
                               // 2 destination: stale infint(p) taken from fix_val[fix_src[e*np+p]]
+  long long fix_n;            // number of entries
   const int *fix_list;        // [entries] point index c*nz+z
   const unsigned long long *fix_need;  // mode 1: [npoints] which p of a source point are wanted
   const int *fix_src;         // mode 2: [entries*np] source entry of each stale p, or -1 (none: 0)
