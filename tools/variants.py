@@ -32,7 +32,7 @@ def build(specs):
 
 def run(out, extra):
     rows = []
-    names = sorted(f[4:-3] for f in os.listdir(VDIR) if f.startswith("lib_") and f.endswith(".so"))
+    names = sorted(f[4:-3] for f in os.listdir(VDIR) if f.startswith("lib_g_") and f.endswith(".so"))
     for name in names:
         env = dict(os.environ, UNC_B200_LIB=os.path.join(VDIR, f"lib_{name}.so"))
         for tag, args in (("full", []), ("nt1", ["--nt", "1"])):
@@ -47,8 +47,23 @@ def run(out, extra):
     open(out, "w").write("\n".join(rows) + "\n")
 
 
+def run_cmd(out, prefix, cmd):
+    """`cmd` once per variant whose name starts with `prefix`; last stdout line of each is kept."""
+    rows = []
+    names = sorted(f[4:-3] for f in os.listdir(VDIR) if f.startswith("lib_" + prefix) and f.endswith(".so"))
+    for name in names:
+        env = dict(os.environ, UNC_B200_LIB=os.path.join(VDIR, f"lib_{name}.so"))
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+        last = (r.stdout.strip().splitlines() or ["FAILED " + r.stderr[-300:]])[-1]
+        rows.append(f"{name:20s} {last}")
+        print(rows[-1], flush=True)
+    open(out, "w").write("\n".join(rows) + "\n")
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "build":
         build(sys.argv[2:])
+    elif sys.argv[1] == "cmd":      # cmd OUT.txt PREFIX command...
+        run_cmd(sys.argv[2], sys.argv[3], sys.argv[4:])
     else:
         run(sys.argv[2], sys.argv[3:])

@@ -351,7 +351,7 @@ int launch_point(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream
   const long long nblk = (nunits + PT - 1) / PT;
   if (nblk <= 0) return UNC_OK;
   if (nblk > 2147483647LL) return fail(UNC_ERR_UNSUPPORTED, "too many work items (%lld)", nblk);
-  unc::lh_point_kernel<ZT, PT><<<(unsigned)nblk, UNC_THREADS, smem, st>>>(P, J);
+  unc::lh_point_kernel<ZT, PT><<<(unsigned)nblk, UNC_PTHREADS, smem, st>>>(P, J);
   g_launches++;
   CK(cudaGetLastError());
   return UNC_OK;
@@ -365,12 +365,18 @@ int launch_zt(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t 
   const long long ntiles = (J.nz + ZT - 1) / ZT;
   const long long nunits = nunits_fix >= 0 ? nunits_fix : J.ncol * ntiles;
   if (ZT == 1) {
+#ifndef UNC_POINT_PTMAX
+#define UNC_POINT_PTMAX 4
+#endif
 #ifndef UNC_BUDGET_SEQSUM
     const int na = P.nts_pad + P.gl_rounds * 32;
-    const long long fill = 2LL * g_ctx[dev].sm_count;
-    if (nunits >= 4 * fill && 2 * unc::point_smem_bytes(P.np, P.nacc, na, 1, 4) <= 227 * 1024)
+    const int cta_per_sm = 16 / UNC_PWARPS;
+    const long long fill = (long long)cta_per_sm * g_ctx[dev].sm_count;
+    if (UNC_POINT_PTMAX >= 4 && nunits >= 4 * fill &&
+        cta_per_sm * unc::point_smem_bytes(P.np, P.nacc, na, 1, 4) <= 227 * 1024)
       return launch_point<1, 4>(dev, P, J, st, nunits);
-    if (nunits >= 2 * fill && 2 * unc::point_smem_bytes(P.np, P.nacc, na, 1, 2) <= 227 * 1024)
+    if (UNC_POINT_PTMAX >= 2 && nunits >= 2 * fill &&
+        cta_per_sm * unc::point_smem_bytes(P.np, P.nacc, na, 1, 2) <= 227 * 1024)
       return launch_point<1, 2>(dev, P, J, st, nunits);
 #endif
     return launch_point<1, 1>(dev, P, J, st, nunits);

@@ -675,8 +675,12 @@ __device__ __forceinline__ bool point_eval(const DevParams &P, cplx pp, cplx aux
   }
 }
 
+#ifndef UNC_PWARPS
+#define UNC_PWARPS 8       // warps per CTA of the point kernel
+#endif
+#define UNC_PTHREADS (UNC_PWARPS * 32)
 #ifndef UNC_POINT_MINB
-#define UNC_POINT_MINB 2   // 128 registers, 16 warps per SM: C5b 481 ms vs 595 ms at 226 registers and 8 warps
+#define UNC_POINT_MINB (16 / UNC_PWARPS)   // 128 registers, 16 warps per SM: C5b 481 ms vs 595 ms at 226 registers and 8 warps
 #endif
 // Work unit = one (t,r) column and a tile of ZT z-values; a CTA takes PT units (PT > 1 only with
 // ZT = 1: scattered points and time series, where the Wynn phase has np and the de Hoog phase
@@ -700,18 +704,18 @@ __host__ __device__ inline size_t point_unit_bytes(int np, int nacc, int na, int
 
 __host__ __device__ inline size_t point_smem_bytes(int np, int nacc, int na, int ZT, int PT) {
   size_t areas = (size_t)PT * np * ZT * nacc * sizeof(cplx);
-  size_t scratch = (size_t)UNC_WARPS * 3 * np * sizeof(cplx);  // de Hoog q,e,d per warp (aliases the areas)
+  size_t scratch = (size_t)UNC_PWARPS * 3 * np * sizeof(cplx);  // de Hoog q,e,d per warp (aliases the areas)
   size_t b = (areas > scratch ? areas : scratch) + (size_t)PT * point_unit_bytes(np, nacc, na, ZT);
   b += (size_t)PT * sizeof(PointUnit);
   b = (b + 15) & ~(size_t)15;
 #ifdef UNC_BUDGET_SEQSUM
-  b += (size_t)UNC_WARPS * na * sizeof(cplx);           // every abscissa's value, per warp
+  b += (size_t)UNC_PWARPS * na * sizeof(cplx);           // every abscissa's value, per warp
 #endif
   return b;
 }
 
 template <int ZT, int PT>
-__global__ void __launch_bounds__(UNC_THREADS, UNC_POINT_MINB)
+__global__ void __launch_bounds__(UNC_PTHREADS, UNC_POINT_MINB)
 lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job J) {
   static_assert(ZT == 1 || PT == 1, "several units per CTA only for one z per unit");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -729,7 +733,7 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
   cplx *s_area_all = (cplx *)sp;
   {
     size_t areas = (size_t)PT * np * ZT * nacc * sizeof(cplx);
-    size_t scratch = (size_t)UNC_WARPS * 3 * np * sizeof(cplx);
+    size_t scratch = (size_t)UNC_PWARPS * 3 * np * sizeof(cplx);
     sp += areas > scratch ? areas : scratch;
   }
   unsigned char *unit_base = sp;
@@ -737,7 +741,7 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
   sp += (size_t)PT * ub;
   PointUnit *s_unit = (PointUnit *)sp;
 #ifdef UNC_BUDGET_SEQSUM
-  cplx *s_seq = (cplx *)(smem_raw + point_smem_bytes(np, nacc, na, ZT, PT)) - (size_t)UNC_WARPS * na + (size_t)warp * na;
+  cplx *s_seq = (cplx *)(smem_raw + point_smem_bytes(np, nacc, na, ZT, PT)) - (size_t)UNC_PWARPS * na + (size_t)warp * na;
 #endif
   struct UnitMem {
     PTab T;
@@ -792,7 +796,7 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
     s_unit[u] = d;
   }
   __syncthreads();
-  for (int k = tid; k < PT * np; k += UNC_THREADS) {
+  for (int k = tid; k < PT * np; k += UNC_PTHREADS) {
     const int u = k / np, i = k - u * np;
     if (!s_unit[u].valid) continue;
     UnitMem m = unit_mem(u);
@@ -818,7 +822,7 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
     m.T.aux[i] = aux;
     m.T.aux2[i] = aux2;
   }
-  for (int k = tid; k < PT * na; k += UNC_THREADS) {
+  for (int k = tid; k < PT * na; k += UNC_PTHREADS) {
     const int u = k / na, idx = k - u * na;
     if (!s_unit[u].valid) continue;
     UnitMem m = unit_mem(u);
@@ -837,9 +841,7 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
 #endif
       }
     } else {
-      const int kk = idx - P.nts_pad;
-      const int L = kk & 31, i = kk >> 5;
-      const int node = L * P.gl_rounds + i;
+      const int node = idx - P.nts_pad;   // a round of phase A = 32 consecutive nodes
       if (node < nacc * G) {
         const int j = node / G, mm = node - j * G;
         const double lob = P.j0z[sv + j - 1] / rD;  // driver.f90:188-193
@@ -855,12 +857,14 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
   __syncthreads();
 
   // ---- phase A: Hankel quadrature sums, one warp per (unit, p) ------------------
+  // A round = 32 CONSECUTIVE abscissae, one per lane, tanh-sinh rounds first, then the
+  // Gauss-Lobatto nodes in interval order.  The abscissae beyond the fast-path bound (literal
+  // path, ~15x the cost) are the largest ones of a point: with consecutive nodes per round they
+  // fill a few whole rounds instead of costing two lanes of EVERY round (the former blocked
+  // mapping, lane <-> 18 consecutive nodes, ran the literal path divergently in all rounds).
   const int rounds = P.gl_rounds;
-  const int node0 = lane * rounds;
-  const int jA = node0 / G;
-  const int iB = (jA + 1) * G - node0;  // first round that falls in interval jA+1
-  const int jA_valid = (node0 < nacc * G) ? jA : -1 - lane;  // distinct ids for empty lanes
-  for (int job = warp; job < PT * np; job += UNC_WARPS) {
+  const int ngl = nacc * G;
+  for (int job = warp; job < PT * np; job += UNC_PWARPS) {
     const int u = job / np, pi = job - u * np;
     const PointUnit un = s_unit[u];
     if (!un.valid) continue;
@@ -873,20 +877,24 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
     int lt_[ZT];
 #pragma unroll
     for (int i = 0; i < ZT; ++i) { zt[i] = m.z[i]; lt_[i] = m.lay[i]; }
-    cplx accT[ZT], accA[ZT], accB[ZT];
+    cplx accT[ZT], run[ZT];
 #pragma unroll
-    for (int i = 0; i < ZT; ++i) { accT[i] = mk(0, 0); accA[i] = mk(0, 0); accB[i] = mk(0, 0); }
+    for (int i = 0; i < ZT; ++i) { accT[i] = mk(0, 0); run[i] = mk(0, 0); }
     const cplx pp = m.T.p[pi], aux = m.T.aux[pi], aux2 = m.T.aux2[pi];
     const int nts_rounds = P.nts_pad / 32;
-    // one abscissa per lane per round: tanh-sinh rounds first, then Gauss-Lobatto rounds
+    cplx *area_p = s_area_all + ((size_t)u * np + pi) * ZT * nacc;
+    int jrun = 0;   // interval whose area is being accumulated in run[] (uniform over the warp)
     // (a source of the carry post-pass only needs the Gauss-Lobatto part)
     for (int i = (fix_mode == 1) ? nts_rounds : 0; i < nts_rounds + rounds; ++i) {
       const bool ts = i < nts_rounds;
-      const int idx = ts ? i * 32 + lane : P.nts_pad + (i - nts_rounds) * 32 + lane;
-      const bool valid = ts ? (idx < P.N) : (node0 + (i - nts_rounds) < nacc * G);
+      const int node = (i - nts_rounds) * 32 + lane;
+      const int idx = ts ? i * 32 + lane : P.nts_pad + node;
+      const bool valid = ts ? (idx < P.N) : (node < ngl);
+      cplx f[ZT];
+#pragma unroll
+      for (int k = 0; k < ZT; ++k) f[k] = mk(0.0, 0.0);
       if (valid) {
         const double w = m.wj[idx], a2v = m.a2[idx];
-        cplx f[ZT];
         // per-abscissa evaluation as a call: 2% faster than inlined (own register allocation)
         if (!point_eval<ZT>(P, pp, aux, aux2, a2v, w, lay_mask, eta_max, zt, lt_, nzt, f)) {
           const cplx eta_l = csqrt_pos(cscalef(mk(pp.re + a2v, pp.im), 1.0 / P.kappa));
@@ -903,43 +911,45 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
             } else f[k] = mk(0.0, 0.0);
         }
 #ifdef UNC_BUDGET_SEQSUM
-        if (ZT == 1) s_seq[ts ? idx : P.N + node0 + (i - nts_rounds)] = f[0];
+        if (ZT == 1) s_seq[ts ? idx : P.N + node] = f[0];
 #endif
-        if (ts) {
+      }
+      if (ts) {
 #pragma unroll
-          for (int k = 0; k < ZT; ++k) accT[k] = caddf(accT[k], f[k]);
-        } else if (i - nts_rounds < iB) {
+        for (int k = 0; k < ZT; ++k) accT[k] = caddf(accT[k], f[k]);
+      } else {
+        // the (at most two, for G >= 32) intervals this round touches, in order
+        const int base = (i - nts_rounds) * 32;
+        const int j_lo = base / G, j_hi = min(base + 31, ngl - 1) / G;
+        const int myj = valid ? node / G : -1;
+        for (int j = j_lo; j <= j_hi; ++j) {
+          if (j != jrun) {
+            if (lane == 0) {
 #pragma unroll
-          for (int k = 0; k < ZT; ++k) accA[k] = caddf(accA[k], f[k]);
-        } else {
+              for (int k = 0; k < ZT; ++k) area_p[k * nacc + jrun] = run[k];
+            }
 #pragma unroll
-          for (int k = 0; k < ZT; ++k) accB[k] = caddf(accB[k], f[k]);
+            for (int k = 0; k < ZT; ++k) run[k] = mk(0.0, 0.0);
+            jrun = j;
+          }
+#pragma unroll
+          for (int k = 0; k < ZT; ++k) {
+            double vr = (myj == j) ? f[k].re : 0.0, vi = (myj == j) ? f[k].im : 0.0;
+            for (int o = 16; o > 0; o >>= 1) { vr += shfl_xor_d(vr, o); vi += shfl_xor_d(vi, o); }
+            run[k] = mk(run[k].re + vr, run[k].im + vi);
+          }
         }
       }
     }
-    // reductions
-    cplx *area_p = s_area_all + ((size_t)u * np + pi) * ZT * nacc;
-    for (int k = lane; k < ZT * nacc; k += 32) area_p[k] = mk(0.0, 0.0);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < ZT; ++k) area_p[k * nacc + jrun] = run[k];
+    }
 #pragma unroll
     for (int k = 0; k < ZT; ++k) {
       double tr = accT[k].re, ti = accT[k].im;
       for (int o = 16; o > 0; o >>= 1) { tr += shfl_xor_d(tr, o); ti += shfl_xor_d(ti, o); }
       if (lane == 0) m.fin[pi * ZT + k] = mk(tr, ti);
-      double ar = accA[k].re, ai = accA[k].im;
-      for (int dlt = 1; dlt < 32; dlt <<= 1) {
-        double orr = shfl_down_d(ar, dlt), oi = shfl_down_d(ai, dlt);
-        int oj = __shfl_down_sync(0xffffffffu, jA_valid, dlt);
-        if (lane + dlt < 32 && oj == jA_valid) { ar += orr; ai += oi; }
-      }
-      int prevj = __shfl_up_sync(0xffffffffu, jA_valid, 1);
-      bool head = (jA_valid >= 0) && (lane == 0 || prevj != jA_valid);
-      __syncwarp();
-      if (head) area_p[k * nacc + jA] = mk(ar, ai);
-      __syncwarp();
-      if (iB < rounds && jA_valid >= 0 && jA + 1 < nacc) {
-        cplx cur = area_p[k * nacc + jA + 1];
-        area_p[k * nacc + jA + 1] = mk(cur.re + accB[k].re, cur.im + accB[k].im);
-      }
     }
 #ifdef UNC_BUDGET_SEQSUM
     // error-budget build: redo the sums sequentially in the reference's order (driver.f90:135-157,
@@ -993,7 +1003,7 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
   __syncthreads();
 
   // ---- phase B: Wynn-epsilon per (unit,p,z), totlap = finint + infint -----------
-  for (int k = tid; k < PT * np * ZT; k += UNC_THREADS) {
+  for (int k = tid; k < PT * np * ZT; k += UNC_PTHREADS) {
     const int u = k / (np * ZT), kk = k - u * (np * ZT);
     const int pi = kk / ZT, zi = kk - pi * ZT;
     if (!s_unit[u].valid) continue;
@@ -1037,7 +1047,7 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
 
   // ---- phase C: de Hoog inversion of value and log-time derivative ------------
   cplx *scr = s_area_all + (size_t)warp * 3 * np;
-  for (int job = warp; job < PT * 2 * ZT; job += UNC_WARPS) {
+  for (int job = warp; job < PT * 2 * ZT; job += UNC_PWARPS) {
     const int u = job / (2 * ZT), jj = job - u * (2 * ZT);
     const int zi = jj >> 1, deriv = jj & 1;
     const PointUnit un = s_unit[u];
