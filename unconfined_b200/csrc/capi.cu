@@ -358,7 +358,7 @@ int launch_point(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream
 }
 
 // ZT z-values of one column per work unit; for ZT = 1 (scattered points, time series) a CTA takes
-// up to four units so that its Wynn and de Hoog phases are full -- when there are enough units to
+// two units so that its Wynn and de Hoog phases are fuller -- when there are enough units to
 // fill the GPU that way and two such CTAs still fit an SM
 template <int ZT>
 int launch_zt(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st, long long nunits_fix = -1) {
@@ -366,7 +366,7 @@ int launch_zt(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t 
   const long long nunits = nunits_fix >= 0 ? nunits_fix : J.ncol * ntiles;
   if (ZT == 1) {
 #ifndef UNC_POINT_PTMAX
-#define UNC_POINT_PTMAX 4
+#define UNC_POINT_PTMAX 2   // C5b, ms per 2^17 points: one unit per CTA 290, two 287, four 318 (instruction-cache misses)
 #endif
 #ifndef UNC_BUDGET_SEQSUM
     const int na = P.nts_pad + P.gl_rounds * 32;
