@@ -291,8 +291,8 @@ void lap_time(const params &prm, const std::vector<cx<T>> &p, std::vector<cx<T>>
 // ---------------------------------------------------------------------------
 // cbessel.f90:877-1146 (cbesk) -> 5036-5495 (cbknu), specialised to fnu=0, kode=1, n=2,
 // Re z >= 0.  Returns ierr as cbesk does; nz_out = number of underflowed members.
-// The exp(-z) underflow branch (Re z > alim, cbessel.f90:5408-5478 -> ckscl) is
-// not restated: it returns ierr=6 (oracle-only code) -- unreachable for rDw*sqrt(p).
+// Includes the exp(-z) underflow branch for Re z > alim (cbessel.f90:5215 -> label 200 :5482,
+// scaled Miller recurrence, label 190 :5458-5466 -> ckscl :5499-5611 -> cuchk :5895-5927).
 inline int cbesk01(cx<double> z, cx<double> K[2], int *nz_out) {
   typedef double R;
   typedef cx<double> C;
@@ -333,7 +333,7 @@ inline int cbesk01(cx<double> z, cx<double> K[2], int *nz_out) {
   const C rz = C(2.0, 0.0) / z;
   const R dnu = 0.0, dnu2 = 0.0;
   C s1, s2;
-  int kflag;
+  int kflag, iflag = 0;
   const R cssv[4] = {0, 1.0 / tol, 1.0, tol}, csrv[4] = {0, tol, 1.0, 1.0 / tol};
   if (caz <= 2.0) {
     // series, cbessel.f90:5098-5200
@@ -385,8 +385,8 @@ inline int cbesk01(cx<double> z, cx<double> K[2], int *nz_out) {
     // Miller, cbessel.f90:5209-5327
     C coef = C(rthpi, 0.0) / csqrt(z);
     kflag = 2;
-    if (xx > alim) return 6;
-    {
+    iflag = (xx > alim) ? 1 : 0;   // cbessel.f90:5215 -> 200: koded = 2, values stay scaled by exp(z)
+    if (!iflag) {
       R a1 = std::exp(-xx) * cssv[kflag];
       C pt = a1 * C(std::cos(yy), -std::sin(yy));
       coef = coef * pt;
@@ -459,6 +459,41 @@ inline int cbesk01(cx<double> z, cx<double> K[2], int *nz_out) {
     p2 = conj(p2) * pt;
     pt = p1 * p2;
     s2 = s1 * (C(1.0, 0.0) + (C(dnu + 0.5, 0.0) - pt) / z);
+  }
+  if (iflag) {
+    // label 100 (inu = 0) -> 190: y = (s1, s2); ckscl with zd = z, n = 2, ascle = bry(1)
+    const R ascle = 1.0e+3f * tiny_ / tol;
+    C y[2] = {s1, s2};
+    int nz = 0, ic = 0;
+    for (int i = 1; i <= 2; ++i) {
+      const C sv = y[i - 1];
+      const R as = cabs(sv);
+      const R acs = -xx + std::log(as);
+      nz += 1;
+      y[i - 1] = C(0.0, 0.0);
+      if (acs >= -elim) {
+        C cs = (-z) + clog(sv);
+        const R aa2 = std::exp(cs.re) / tol;
+        cs = aa2 * C(std::cos(cs.im), std::sin(cs.im));
+        // cuchk
+        int nw = 0;
+        const R yr = std::fabs(cs.re), yi = std::fabs(cs.im);
+        R st = std::min(yr, yi);
+        if (!(st > ascle)) {
+          const R ss = std::max(yr, yi);
+          st = st / tol;
+          if (ss < st) nw = 1;
+        }
+        if (nw == 0) { y[i - 1] = cs; nz -= 1; ic = i; }
+      }
+    }
+    if (ic <= 1) { y[0] = C(0.0, 0.0); nz = 2; }
+    // back in cbknu (:5467-5476): the surviving members are unscaled by csr(1) = tol
+    K[0] = C(0.0, 0.0); K[1] = C(0.0, 0.0);
+    if (nz == 0) { K[0] = y[0] * C(csrv[1], 0.0); K[1] = y[1] * C(csrv[1], 0.0); }
+    else if (nz == 1) { K[1] = y[1] * C(csrv[1], 0.0); }
+    *nz_out = nz;
+    return ierr;
   }
   // label 100 -> 130 (inu=0, n=2)
   K[0] = s1 * C(csrv[kflag], 0.0);

@@ -388,3 +388,47 @@ def test_model6_small_radius_where_delta0_squared_overflows():
         ub.force_kernel(kernel)
         sg, dg = ub.eval_grid(ub.Params(pq), *args)
         check_parity(sg, dg, so, do, sps, spd, what=f"model 6 small rD [{kernel}]")
+
+
+def test_device_cbknu_all_branches_against_the_oracle_and_scipy():
+    """cbesk -> cbknu for fnu=0, n=2 on the device (kernels.cuh cbesk01_dev): power series (|z| <= 2),
+    Miller recurrence, and the exp(-z) underflow branch through ckscl/cuchk (Re z > 664.87,
+    cbessel.f90:5215,5458-5476,5499-5611): against the oracle's restatement (itself bitwise equal to
+    scipy's Amos there) to a few ulp, underflowed members exactly zero in both."""
+    from scipy.special import kv
+    rng = np.random.default_rng(3)
+    z = np.concatenate([rng.uniform(0.01, 2, 40) * np.exp(1j * rng.uniform(-1.5, 1.5, 40)),
+                        rng.uniform(2, 60, 60) * np.exp(1j * rng.uniform(-1.5, 1.5, 60)),
+                        rng.uniform(60, 664, 40) + 1j * rng.uniform(-300, 300, 40),
+                        rng.uniform(665, 697, 40) + 1j * rng.uniform(-300, 300, 40),
+                        rng.uniform(698.5, 1500, 20) + 1j * rng.uniform(-300, 300, 20),
+                        [670.0 + 0j, 664.9 + 0.1j, 697.0 + 1j]])
+    k0, k1 = ub.debug_cbesk01(z)
+    for i, zz in enumerate(z):
+        o0, o1, ierr, nz = oracle.cbesk01(complex(zz))
+        assert ierr in (0, 3)
+        for got, want in ((k0[i], o0), (k1[i], o1)):
+            if want == 0:
+                assert got == 0, (zz, got)
+            else:
+                assert abs(got - want) <= 3e-14 * abs(want), (zz, got, want)
+        if 2.0 < abs(zz) and zz.real < 697.0:
+            assert abs(o0 - kv(0, zz)) <= 1e-15 * abs(o0)
+    assert (k0[-23:-3] == 0).all() and (k0[-63:-23] != 0).all()
+
+
+def test_storage_model_where_k0_k1_underflow():
+    """Model 2 with a wide well at very early time: rDw sqrt(p) runs from ~450 to ~1000 over the
+    Laplace parameters, through cbknu's scaled branch and into complete underflow (K = 0, so
+    A0 = 2/0): the same data-level flow as the oracle."""
+    d, pd = load_deck("hantush-storage-input.dat")
+    q = dict(pd, rDw=0.2, rDwobs=0.2)
+    tD = np.array([1e-6, 3e-6]); sv = np.array([1, 1], np.int32)
+    xi = q["rDw"] * np.sqrt(oracle.pvalues(oracle.Params(q), 2 * tD[0]))
+    assert xi.real.min() < 600 and xi.real.max() > 700
+    args = (tD, sv, np.array([0.05, 0.21]), d["zD"], d["zLay"])
+    so, do, sps, spd = oracle_with_noise(oracle.Params(q), args, nsamples=3)
+    _, _, fo = oracle.eval_grid(oracle.Params(q), *args, carry=False)
+    sg, dg, fg = ub.eval_grid(ub.Params(q), *args, want_flags=True)
+    assert np.array_equal(fo, fg)
+    check_parity(sg, dg, so, do, sps, spd, what="storage underflow")

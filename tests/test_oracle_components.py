@@ -246,3 +246,25 @@ def test_oracle_converges_to_independent_mpmath_values():
             err[tag] = abs(s.ravel()[0] - t["s_D"]) / t["s_D"]
         assert err["deck"] < 2e-3, (t["deck"], err)
         assert err["fine"] < 5e-5 and err["fine"] < err["deck"], (t["deck"], err)
+
+
+def test_cbknu_underflow_branch_equals_scipy_amos():
+    """Re z > alim = 664.87: cbknu keeps the values scaled by exp(z) and ckscl/cuchk decide which
+    members underflow (cbessel.f90:5215,5458-5476,5499-5611,5895-5927).  scipy.special.kv wraps the
+    same Amos routines in double precision: the restatement must agree with it to rounding and
+    underflow to exact zeros where it does."""
+    from scipy.special import kv
+    rng = np.random.default_rng(5)
+    zs = np.concatenate([rng.uniform(665, 697.5, 200) + 1j * rng.uniform(-400, 400, 200),
+                         rng.uniform(698.5, 2000, 50) + 1j * rng.uniform(-400, 400, 50)])
+    nzero = 0
+    for z in zs:
+        k0, k1, ierr, nz = oracle.cbesk01(complex(z))
+        assert ierr in (0, 3)
+        for got, want in ((k0, kv(0, z)), (k1, kv(1, z))):
+            if want == 0:
+                assert got == 0
+                nzero += 1
+            else:
+                assert abs(got - want) <= 4e-16 * abs(want), (z, got, want)
+    assert nzero >= 100

@@ -10,5 +10,5 @@ evaluation call raises if the library or a CUDA device is missing.
 from .api import (UncParams, Params, UncError, lib, eval_grid, eval_points, eval_points_device,  # noqa: F401
                   eval_grid_device, j0_zeros, split_index, zlay, device_count, set_device,
                   measure_fp64_peak, device_info, kernel_launch_count, shutdown, last_error,
-                  set_carry, force_kernel)
+                  set_carry, force_kernel, debug_cbesk01)
 from .build import build  # noqa: F401

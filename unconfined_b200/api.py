@@ -236,3 +236,11 @@ _KERNELS = {None: 0, "auto": 0, "point": 1, "grid": 2, "grid2": 3}
 def force_kernel(which=None):
     """Test hook (unc_debug_force_kernel): None/'auto', 'point', 'grid', 'grid2'."""
     _ck(lib().unc_debug_force_kernel(_KERNELS[which]))
+
+
+def debug_cbesk01(z):
+    """Test hook (unc_debug_cbesk01): K0(z), K1(z) by the device routine for an array of complex z."""
+    z = np.ascontiguousarray(z, np.complex128)
+    out = np.empty((len(z), 2), np.complex128)
+    _ck(lib().unc_debug_cbesk01(len(z), _dp(z.view(np.float64)), _dp(out.view(np.float64))))
+    return out[:, 0], out[:, 1]

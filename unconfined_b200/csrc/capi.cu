@@ -133,7 +133,7 @@ struct HostPlan {
   size_t off_T, off_wc, off_glx, off_glw, off_j0z, off_tp, off_mg, off_lw;
 };
 
-int make_plan(const unc_params *prm, HostPlan &hp) {
+int build_plan(const unc_params *prm, HostPlan &hp) {
   if (!prm) return fail(UNC_ERR_BAD_ARG, "prm is NULL");
   if (prm->model < 0 || prm->model > 6) return fail(UNC_ERR_BAD_ARG, "invalid model %d", prm->model);
   if (prm->model == 6) {
@@ -248,6 +248,44 @@ int make_plan(const unc_params *prm, HostPlan &hp) {
     hp.off_lw = push(all.data(), all.size());
     P.ts_k = prm->ts_k;
   }
+  return UNC_OK;
+}
+
+// The plan depends on the parameter struct only (quadrature set-up: ~250 libm calls and a
+// Newton iteration, ~0.1 ms -- a third of the wall time of a 100-point deck), so the last one
+// is kept.  Callers hold g_mutex.
+struct PlanCache {
+  bool valid = false;
+  unc_params key;
+  std::vector<double> j0z, tp, mg;
+  HostPlan plan;
+};
+PlanCache g_plan_cache;
+
+int make_plan(const unc_params *prm, HostPlan &hp) {
+  if (!prm) return fail(UNC_ERR_BAD_ARG, "prm is NULL");
+  PlanCache &c = g_plan_cache;
+  if (c.valid) {
+    unc_params k = *prm;
+    k.j0z = nullptr; k.time_par = nullptr; k.moench_gamma = nullptr;
+    const bool same = std::memcmp(&k, &c.key, sizeof k) == 0 && prm->j0z && prm->time_par &&
+                      (int)c.j0z.size() == prm->n_j0z && (int)c.tp.size() == prm->n_time_par &&
+                      std::equal(c.j0z.begin(), c.j0z.end(), prm->j0z) &&
+                      std::equal(c.tp.begin(), c.tp.end(), prm->time_par) &&
+                      (c.mg.empty() || (prm->moench_gamma && std::equal(c.mg.begin(), c.mg.end(), prm->moench_gamma)));
+    if (same) { hp = c.plan; return UNC_OK; }
+  }
+  int rc = build_plan(prm, hp);
+  if (rc) return rc;
+  std::memset(&c.key, 0, sizeof c.key);
+  c.key = *prm;
+  c.key.j0z = nullptr; c.key.time_par = nullptr; c.key.moench_gamma = nullptr;
+  c.j0z.assign(prm->j0z, prm->j0z + prm->n_j0z);
+  c.tp.assign(prm->time_par, prm->time_par + prm->n_time_par);
+  c.mg.clear();
+  if (hp.P.moench_M > 0) c.mg.assign(prm->moench_gamma, prm->moench_gamma + hp.P.moench_M);
+  c.plan = hp;
+  c.valid = true;
   return UNC_OK;
 }
 
@@ -674,16 +712,12 @@ int run_shard(const unc_params *prm, const HostJob &hj, Shard &sh) {
   J.s = d_s; J.ds = d_ds;
   J.flags = hj.flags ? d_fl : nullptr;
   J.smask = hj.carry ? d_mask : nullptr;
+  J.nstale = hj.carry ? d_cnt : nullptr;      // the kernels count the points with a stale infint
+  if (hj.carry) CK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned int), st));
   rc = launch(sh.dev, r, hp.P, J, st);
   if (rc) return rc;
   unsigned int h_cnt = 0;
-  if (hj.carry) {
-    CK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned int), st));
-    unc::carry_list_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(d_mask, (long long)npts, nullptr,
-                                                                            nullptr, d_cnt);
-    g_launches++;
-    CK(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-  }
+  if (hj.carry) CK(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(hj.s + sh.c0 * nz, d_s, npts * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(hj.ds + sh.c0 * nz, d_ds, npts * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (hj.flags)
@@ -888,6 +922,27 @@ int unc_shutdown(void) {
  * and UNC_FLAG_STALE_INFINT only, as calls with ts_abscissa_scale = NULL always do */
 int unc_set_carry(int32_t on) {
   g_carry.store(on ? 1 : 0);
+  return UNC_OK;
+}
+
+/* test hook: the device cbknu (K0, K1 of n complex arguments, host arrays z[2n] -> out[4n]) */
+int unc_debug_cbesk01(int32_t n, const double *z, double *out) {
+  if (n < 0 || (n > 0 && (!z || !out))) return fail(UNC_ERR_BAD_ARG, "bad arguments");
+  if (n == 0) return UNC_OK;
+  std::lock_guard<std::mutex> lk(g_mutex);
+  DeviceGuard guard;
+  if (device_count() <= 0) return fail(UNC_ERR_NO_DEVICE, "no CUDA device available");
+  int rc = ensure_ctx(g_device);
+  if (rc) return rc;
+  cudaStream_t st = g_ctx[g_device].stream;
+  double *d = nullptr;
+  CK(cudaMalloc(&d, (size_t)n * 6 * sizeof(double)));
+  CK(cudaMemcpyAsync(d, z, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  unc::cbesk01_test_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, d, d + 2 * (size_t)n);
+  g_launches++;
+  CK(cudaMemcpyAsync(out, d + 2 * (size_t)n, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  cudaFree(d);
   return UNC_OK;
 }
 

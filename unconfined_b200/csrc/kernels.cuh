@@ -78,7 +78,9 @@ __device__ __noinline__ cplx laptime_dev(const DevParams &P, cplx p) {
 // ---------------------------------------------------------------------------
 // cbessel.f90:877-1146 (cbesk) -> 5036-5495 (cbknu) for fnu=0, kode=1, n=2, Re z >= 0.
 // K[0]=K0(z), K[1]=K1(z).  Out-of-range arguments give NaN (the reference prints ierr
-// and carries on with whatever cy holds, laplace_hankel_solutions.f90:259-262).
+// and carries on with whatever cy holds, laplace_hankel_solutions.f90:259-262).  Re z > alim
+// takes the exp(-z) underflow branch (cbessel.f90:5215 -> 200 :5482, 190 :5458-5476, ckscl
+// :5499-5611, cuchk :5895-5927): members that underflow come back as exact zeros.
 __device__ __noinline__ void cbesk01_dev(cplx z, cplx *K) {
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
   const double tol = 2.220446049250313e-16;
@@ -96,6 +98,7 @@ __device__ __noinline__ void cbesk01_dev(cplx z, cplx *K) {
   const cplx rz = mk(2.0, 0.0) / z;
   cplx s1, s2;
   double csr = 1.0;
+  bool iflag = false;
   if (caz <= 2.0) {
     // power series, cbessel.f90:5098-5200 with dnu=0: fc=1, t1=t2=1, g1=-cc(1), g2=1
     cplx smu = clog_g(rz);
@@ -128,9 +131,9 @@ __device__ __noinline__ void cbesk01_dev(cplx z, cplx *K) {
     s1 = s1 * mk(css, 0.0);
   } else {
     // Miller backward recurrence, cbessel.f90:5209-5327
-    if (xx > alim) return;  // exp(-z) underflow branch (ckscl) not implemented: NaN
+    iflag = xx > alim;      // koded = 2: the values stay scaled by exp(z) until ckscl
     cplx coef = mk(rthpi, 0.0) / csqrt_g(z);
-    {
+    if (!iflag) {
       double a1 = exp(-xx);
       cplx pt = a1 * mk(cos(yy), -sin(yy));
       coef = coef * pt;
@@ -202,6 +205,39 @@ __device__ __noinline__ void cbesk01_dev(cplx z, cplx *K) {
     p2 = conj(p2) * pt;
     pt = p1 * p2;
     s2 = s1 * (mk(1.0, 0.0) + (mk(0.5, 0.0) - pt) / z);
+  }
+  if (iflag) {
+    // ckscl with zd = z, n = 2, ascle = bry(1) = 1e3*tiny/tol; survivors unscaled by csr(1) = tol
+    const double ascle = 1.0e3 * DBL_MIN / tol;
+    cplx y[2] = {s1, s2};
+    int nz = 0, ic = 0;
+#pragma unroll
+    for (int i = 1; i <= 2; ++i) {
+      const cplx sv = y[i - 1];
+      const double as = cabs_d(sv);
+      const double acs = -xx + log(as);
+      nz += 1;
+      y[i - 1] = mk(0.0, 0.0);
+      if (acs >= -elim) {
+        cplx cs = (-z) + clog_g(sv);
+        const double aa2 = exp(cs.re) / tol;
+        cs = aa2 * mk(cos(cs.im), sin(cs.im));
+        int nw = 0;
+        const double yr = fabs(cs.re), yi = fabs(cs.im);
+        double st = fmin(yr, yi);
+        if (!(st > ascle)) {
+          const double ss = fmax(yr, yi);
+          st = st / tol;
+          if (ss < st) nw = 1;
+        }
+        if (nw == 0) { y[i - 1] = cs; nz -= 1; ic = i; }
+      }
+    }
+    if (ic <= 1) { y[0] = mk(0.0, 0.0); nz = 2; }
+    K[0] = mk(0.0, 0.0); K[1] = mk(0.0, 0.0);
+    if (nz == 0) { K[0] = y[0] * mk(tol, 0.0); K[1] = y[1] * mk(tol, 0.0); }
+    else if (nz == 1) K[1] = y[1] * mk(tol, 0.0);
+    return;
   }
   K[0] = s1 * mk(csr, 0.0);
   K[1] = s2 * mk(csr, 0.0);
@@ -1068,6 +1104,7 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
         J.s[o] = v;
         if (J.flags) J.flags[o] = m.mask[zi] != 0ull ? 1 : 0;
         if (J.smask) J.smask[o] = m.mask[zi];
+        if (J.nstale && m.mask[zi] != 0ull) atomicAdd(J.nstale, 1u);
       }
     }
     __syncwarp();
@@ -1343,6 +1380,7 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
         J.s[o] = v;
         if (J.flags) J.flags[o] = fl != 0ull ? 1 : 0;
         if (J.smask) J.smask[o] = fl;
+        if (J.nstale && fl != 0ull) atomicAdd(J.nstale, 1u);
       }
     }
     __syncwarp();
@@ -1876,6 +1914,7 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
             J.s[o] = v;
             if (J.flags) J.flags[o] = flag_prev[zi] != 0ull ? 1 : 0;
             if (J.smask) J.smask[o] = flag_prev[zi];
+            if (J.nstale && flag_prev[zi] != 0ull) atomicAdd(J.nstale, 1u);
           }
         }
         __syncwarp();
@@ -2052,6 +2091,15 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
   }
 }
 
+
+// test hook (unc_debug_cbesk01): K0, K1 of n complex arguments by the device routine
+__global__ void cbesk01_test_kernel(int n, const double *z, double *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  cplx K[2];
+  cbesk01_dev(mk(z[2 * i], z[2 * i + 1]), K);
+  out[4 * i] = K[0].re; out[4 * i + 1] = K[0].im; out[4 * i + 2] = K[1].re; out[4 * i + 3] = K[1].im;
+}
 
 // DFMA-chain microbenchmark: 8 independent chains per thread
 __global__ void fp64_peak_kernel(double *out, int iters) {

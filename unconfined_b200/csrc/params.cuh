@@ -42,6 +42,7 @@ struct Job {
   double *s, *ds;
   int *flags;
   unsigned long long *smask;  // per point, or NULL: bit p set = infint(p,z) was stale (driver.f90:209)
+  unsigned int *nstale;       // or NULL: incremented once per point with a non-zero mask
   // carry post-pass (lh_point_kernel<1> only; capi.cu carry_postpass): CTA e works on point fix_list[e]
   int fix_mode;               // 0 normal; 1 source: Wynn result of the p in need[] -> fix_val;
                               // 2 destination: stale infint(p) taken from fix_val[fix_src[e*np+p]]
