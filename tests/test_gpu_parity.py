@@ -15,7 +15,11 @@ pytestmark = pytest.mark.gpu
 DECKS = ["theis-input.dat", "hantush-input.dat", "cape-cod-neuman74.in", "cape-cod-moench.in",
          "malama-partpen-input.dat", "malama-fullpen-input.dat", "hantush-storage-input.dat",
          "hantush-fullpen-test.in", "theis-contours-input.dat", "hantush-contours-input.dat",
-         "mishra-neuman-malama.in"]
+         "mishra-neuman-malama.in",
+         # further decks of the reference with numerics of their own: k=10, R=8, ord=40 / M=18;
+         # tol=1e-12; screened observation wells (nz=2); beta=1; pulse pumping with ord=100
+         "malama-test-input.dat", "cape-cod-compare-malama.in", "cape-cod-early.in", "cape-cod-late.in",
+         "cape-cod-malama.in", "gi-71A.in"]
 
 
 @pytest.fixture(autouse=True)
@@ -413,7 +417,7 @@ def test_device_cbknu_all_branches_against_the_oracle_and_scipy():
             else:
                 assert abs(got - want) <= 3e-14 * abs(want), (zz, got, want)
         if 2.0 < abs(zz) and zz.real < 697.0:
-            assert abs(o0 - kv(0, zz)) <= 1e-15 * abs(o0)
+            assert abs(o0 - kv(0, zz)) <= 1e-12 * abs(o0)
     assert (k0[-23:-3] == 0).all() and (k0[-63:-23] != 0).all()
 
 
