@@ -15,7 +15,7 @@ module unconfined_b200
   public :: unc_params, unc_eval_grid, unc_eval_grid_ex, unc_eval_points, unc_eval_points_ex, &
        & unc_j0_zeros, unc_split_index, unc_zlay, unc_device_count, unc_set_device, &
        & unc_device_info, unc_measure_fp64_peak, unc_kernel_launch_count, unc_shutdown, &
-       & unc_last_error, unc_fill_params
+       & unc_set_carry, unc_last_error, unc_fill_params
 
   integer(c_int), parameter, public :: UNC_OK = 0, UNC_ERR_BAD_ARG = -1, UNC_ERR_UNSUPPORTED = -2, &
        & UNC_ERR_NO_DEVICE = -3, UNC_ERR_CUDA = -4, UNC_ERR_IO = -5
@@ -135,6 +135,13 @@ module unconfined_b200
      integer(c_int) function unc_shutdown() bind(C, name='unc_shutdown')
        import :: c_int
      end function unc_shutdown
+
+     ! default 1: grid calls that pass ts_scale also reproduce the reference's stale infint
+     ! (driver.f90:205-214); 0: such points get infint = 0 (and the flag) only
+     integer(c_int) function unc_set_carry(on) bind(C, name='unc_set_carry')
+       import :: c_int, c_int32_t
+       integer(c_int32_t), value :: on
+     end function unc_set_carry
 
      type(c_ptr) function unc_last_error_c() bind(C, name='unc_last_error')
        import :: c_ptr
