@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libunconfined_b200.so")
 SOURCES = ["capi.cu"]
-HEADERS = ["kernels.cuh", "cmath.cuh", "fast.cuh", "wynn.cuh", "params.cuh", "j0_table.h",
+HEADERS = ["kernels.cuh", "grid8.cuh", "carry.cuh", "cmath.cuh", "fast.cuh", "wynn.cuh", "params.cuh", "j0_table.h",
            os.path.join("..", "..", "include", "unconfined_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

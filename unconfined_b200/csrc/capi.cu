@@ -444,27 +444,29 @@ int launch_grid_zl(int dev, const unc::DevParams &P, const unc::Job &J, cudaStre
 // 128 z per work item, persistent CTAs drawing items from an atomic counter, eight z-slots per
 // lane and two Laplace parameters per warp; totlap in a per-CTA global scratch slot
 // (kernels.cuh: lh_grid8_kernel).  Scratch and counter belong to the launch stream.
+// 128 z per work item, persistent CTAs drawing items from an atomic counter, eight z-slots per
+// lane and two Laplace parameters per warp; totlap and the items' tables in per-CTA global
+// scratch slots (grid8.cuh: lh_grid8_kernel).  Scratch and counter belong to the launch stream.
 template <int NW>
 int launch_grid8_nw(int dev, StreamRes &r, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
-  const int NA = P.N + P.nacc * P.G;
-  const size_t smem = unc::grid8_smem_bytes(P.np, (NA + 31) & ~31, NW);
+  const int NA = P.N + P.nacc * P.G, na_seq = (NA + 31) & ~31;
+  const size_t smem = unc::grid8_smem_bytes(P.np, na_seq, NW);
   if (smem > 227 * 1024) return fail(UNC_ERR_UNSUPPORTED, "shared memory need %zu B exceeds 227 KB", smem);
   DevCtx &c = g_ctx[dev];
   if (!c.smem_set[20]) {
     CK(cudaFuncSetAttribute(unc::lh_grid8_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-#ifdef UNC_CARVEOUT   // measured (ms/step): default 111.7 = 60 (132 KB shared, 124 KB L1); 100 (28 KB L1) 115.8
-    CK(cudaFuncSetAttribute(unc::lh_grid8_kernel<NW>, cudaFuncAttributePreferredSharedMemoryCarveout, UNC_CARVEOUT));
-#endif
     c.smem_set[20] = true;
   }
   const long long nitems = J.ncol * ((J.nz + 127) / 128);
   if (nitems <= 0) return UNC_OK;
   if (nitems > 4000000000LL) return fail(UNC_ERR_UNSUPPORTED, "too many work items (%lld)", nitems);
-  int occ = 2;
+  int occ = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, unc::lh_grid8_kernel<NW>, NW * 32, smem));
   if (occ < 1) occ = 1;
   const int grid = (int)std::min<long long>(nitems, (long long)c.sm_count * occ);
-  int rc = r.scratch.ensure((size_t)grid * 2 * P.np * 128 * sizeof(unc::cplx));   // two totlap slots per CTA
+  // per CTA: three totlap slots and two table slots
+  const size_t tab_bytes = (size_t)4 * P.np * sizeof(unc::cplx) + (size_t)2 * na_seq * sizeof(double);
+  int rc = r.scratch.ensure((size_t)grid * 3 * P.np * 128 * sizeof(unc::cplx) + (size_t)grid * 2 * tab_bytes);
   if (rc) return rc;
   rc = r.counter.ensure(256);
   if (rc) return rc;
@@ -480,11 +482,7 @@ int launch_grid8_nw(int dev, StreamRes &r, const unc::DevParams &P, const unc::J
 
 int launch_grid(int dev, StreamRes &r, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
   const bool small_only = g_force.load() == 3;
-#ifdef UNC_GRID8_NW
-  if (J.nz >= 96 && !small_only) return launch_grid8_nw<UNC_GRID8_NW>(dev, r, P, J, st);   // experiments
-#else
-  if (J.nz >= 96 && !small_only) return launch_grid8_nw<8>(dev, r, P, J, st);
-#endif
+  if (J.nz >= 96 && !small_only) return launch_grid8_nw<UNC_GRID8_NW>(dev, r, P, J, st);
   // two z per lane (64 z per CTA) halves the per-(a,p) work per point; keep one z per lane
   // for short columns and when the larger totlap tile would not fit twice per SM
   if (J.nz > 32 && P.np <= 53) return launch_grid_zl<2>(dev, P, J, st);

@@ -1388,24 +1388,6 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
 }
 
 // ---------------------------------------------------------------------------
-// clock64 phase timers of the persistent grid kernel (-DUNC_PROFILE builds, tools/prof_run.py)
-#ifdef UNC_PROFILE
-__device__ unsigned long long g_prof[16];
-// clock read with a memory clobber: it must not be scheduled across the barriers it brackets
-__device__ __forceinline__ long long prof_clock() {
-  long long t;
-  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : : "memory");
-  return t;
-}
-#define PROF_T0() long long _t0 = prof_clock()
-#define PROF_ADD(i) do { long long _t1 = prof_clock(); if (lane == 0) atomicAdd(&g_prof[i], (unsigned long long)(_t1 - _t0)); _t0 = _t1; } while (0)
-#else
-#define PROF_T0()
-#define PROF_ADD(i)
-#endif
-
-
-// ---------------------------------------------------------------------------
 // Eight z-slots per lane, two Laplace parameters per warp (lh_grid8_kernel below).
 struct StageEnt8 {
   cplx eta;
@@ -1688,410 +1670,6 @@ __device__ __forceinline__ int ap_terms_stage8(const DevParams &P, cplx p, cplx 
 #endif
 }
 
-__host__ __device__ inline size_t grid8_smem_bytes(int np, int na_seq, int NW) {
-  size_t b = 0;
-  b += (size_t)4 * np * sizeof(cplx);
-  b += (size_t)2 * na_seq * sizeof(double);
-  size_t stage = (size_t)NW * 32 * sizeof(StageEnt8) + (size_t)NW * 32 * sizeof(int);
-  size_t scratch = (size_t)NW * 3 * np * sizeof(cplx);
-  b += stage > scratch ? stage : scratch;
-  b += 2 * 128 * sizeof(unsigned long long) + 64;
-  return (b + 15) & ~(size_t)15;
-}
-
-#ifndef UNC_GRID8_MINB
-#define UNC_GRID8_MINB 2
-#endif
-
-// ---------------------------------------------------------------------------
-// Grid kernel for contour grids (nz >= 96): persistent CTAs draw work items (one (t,r) column x
-// up to 128 z) from a global atomic counter, so the few expensive columns (literal path at
-// small rD) do not leave SMs idle.  Lanes <-> z with EIGHT z-slots per lane and TWO Laplace
-// parameters per warp (lanes 0-15 <-> p = 2*job, lanes 16-31 <-> p = 2*job+1; z = z0 + hl +
-// 16 k): the per-(a,p) terms are staged in shared memory 16 abscissae at a time and shared by
-// 128 z, the per-abscissa exponential of slot 0 (48 of the FP64 instructions) by eight z, and
-// the slots advance the products cp*e^{eta z}, cm*e^{-eta z} themselves (eval8_scaled).
-// Requires equally spaced z within an item, checked per item on the actual z (tolerance 4 ulp
-// of max|z|: the induced error |eta|*4ulp is the size of the reference's own rounding of the
-// product eta*zD); any other z-list takes the exact per-slot evaluation.  totlap (np x 128
-// complex = 108 KB for M=26) lives in a global scratch slot owned by the CTA (L2-resident)
-// instead of shared memory, which keeps 2 CTAs (16 warps) per SM.
-//
-// Measured and NOT kept (round 2, C5a, same box): the same jobs in ONE linear sequence without
-// CTA-wide barriers (table-building job per item, completion counters, tables double- and
-// totlap/descriptors triple-buffered; commit 8f5bba8): 98.7 ms against 91.9 ms.  The barrier's
-// 6-7 % of stall samples is time in which the SM's other CTA has the FP64 pipe to itself; what the
-// variant paid for was shared memory (91 KB per CTA instead of 75 KB leaves 60 KB instead of
-// 92 KB of L1 for the thread-local area/q-d arrays).  With one 16-warp CTA per SM both designs
-// run at 94.1 ms.
-template <int NW>
-__global__ void __launch_bounds__(NW * 32, UNC_GRID8_MINB)
-lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job J,
-                cplx *__restrict__ g_tot, unsigned int *__restrict__ g_counter) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int ZL = 8, ZB = 128, GL = 16;   // 8 slots per lane, 16 lanes per Laplace parameter
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int half = lane >> 4, hl = lane & 15;   // which of the warp's two p; z lane
-  const int np = P.np, nacc = P.nacc, G = P.G, N = P.N;
-  const int NA = N + nacc * G;
-  const int na_seq = (NA + 31) & ~31;
-  const int nzb = (J.nz + ZB - 1) / ZB;
-  const long long nitems = J.ncol * (long long)nzb;
-
-  unsigned char *sp = smem_raw;
-  PTab T;
-  T.p = (cplx *)sp; sp += np * sizeof(cplx);
-  T.lt = (cplx *)sp; sp += np * sizeof(cplx);
-  T.aux = (cplx *)sp; sp += np * sizeof(cplx);
-  T.aux2 = (cplx *)sp; sp += np * sizeof(cplx);
-  double *s_a2 = (double *)sp; sp += na_seq * sizeof(double);
-  double *s_wj = (double *)sp; sp += na_seq * sizeof(double);
-  StageEnt8 *s_stage = (StageEnt8 *)sp;
-  int *s_ok = (int *)(sp + (size_t)NW * 32 * sizeof(StageEnt8));
-  cplx *s_scr = (cplx *)sp;
-  {
-    size_t stage = (size_t)NW * 32 * sizeof(StageEnt8) + (size_t)NW * 32 * sizeof(int);
-    size_t scratch = (size_t)NW * 3 * np * sizeof(cplx);
-    sp += stage > scratch ? stage : scratch;
-  }
-  unsigned long long *s_flag = (unsigned long long *)sp; sp += 2 * 128 * sizeof(unsigned long long);   // stale masks (bit p) per z, [buffer][z]
-  int *s_misc = (int *)sp;  // [0] layer mask, [1] max|z| bits, [2] uniform-z flag, [3] item, [6..7] D, [8] job counter
-  cplx *tot_base = g_tot + (size_t)blockIdx.x * 2 * np * ZB;  // this CTA's two totlap slots [p][z]
-
-  // Software pipeline over work items: round i runs the np quadrature jobs ("p-jobs") of
-  // item i AND the de Hoog jobs ("D-jobs", 32 inversions each, one per lane) of item i-1 out
-  // of one job pool that the warps drain through a shared-memory counter.  The small D-jobs
-  // come last, so the warps that run out of p-jobs invert the previous item's totlap while
-  // the others finish: no separate de Hoog phase with every warp stalled on its q-d table,
-  // and the end-of-round barrier waits for a D-job at most, not for a p-job.
-  int buf = 0;
-  bool have_prev = false, dry = false;
-  long long prev_col = 0;
-  int prev_z0 = 0, prev_nzv = 0;
-  double prev_tD = 0.0;
-  PROF_T0();
-  for (;;) {
-    __syncthreads();   // every job of the previous round is complete
-    PROF_ADD(0);
-    if (tid == 0) {
-      if (!dry) s_misc[3] = (int)atomicAdd(g_counter, 1u);
-      s_misc[8] = 0;
-    }
-    __syncthreads();
-    PROF_ADD(7);
-    const long long item = (unsigned int)s_misc[3];
-    const bool have_cur = item < nitems;
-    if (!have_cur) dry = true;
-    if (!have_cur && !have_prev) {
-      // the last CTA to finish re-arms both counters, so every launch (and every profiler
-      // replay of a launch) starts from zero without a host-side memset
-      if (tid == 0) {
-        __threadfence();
-        if (atomicAdd(g_counter + 1, 1u) == gridDim.x - 1) {
-          g_counter[0] = 0u;
-          g_counter[1] = 0u;
-          __threadfence();
-        }
-      }
-      break;
-    }
-    cplx *tot = tot_base + (size_t)buf * np * ZB;
-    const cplx *tot_prev = tot_base + (size_t)(buf ^ 1) * np * ZB;
-    unsigned long long *flag_cur = s_flag + buf * 128;
-    const unsigned long long *flag_prev = s_flag + (buf ^ 1) * 128;
-
-    const long long col = have_cur ? item / nzb : 0;
-    const int z0 = have_cur ? (int)(item % nzb) * ZB : 0;
-    const int nzv = have_cur ? min(ZB, J.nz - z0) : 0;
-    const long long tcol = col + J.col0;
-    const double tD = J.tD[tcol / J.tdiv];
-    const int sv = J.sv[tcol / J.tdiv];
-    const double rD = J.rD[tcol % J.rmod];
-    const double tee = P.tee_mult * tD;
-    const double arg = P.j0z[sv - 1] / rD;                      // driver.f90:120
-    const double tscale = J.ts_scale ? J.ts_scale[col] : arg;  // driver.f90:121-126
-    const long long zbase = (J.zstride ? col * (long long)J.nz : 0) + z0;
-    double myz[ZL];
-    int mylay[ZL];
-    bool zvalid[ZL];
-#pragma unroll
-    for (int k = 0; k < ZL; ++k) {
-      const int zi = hl + GL * k;
-      zvalid[k] = zi < nzv;
-      myz[k] = zvalid[k] ? J.zD[zbase + zi] : 0.0;
-      mylay[k] = zvalid[k] ? J.zLay[zbase + zi] : 0;
-    }
-
-    // ---- prologue (tables of the current item) -----------------------------------
-    PROF_ADD(8);
-    if (have_cur) {
-      if (tid < ZB) flag_cur[tid] = 0ull;
-      item_tables(P, T, s_a2, s_wj, tD, sv, rD, tscale, tid, NW * 32);
-      PROF_ADD(9);
-      if (warp == 0) {
-        int m = 0;
-        float za = 0.f;
-#pragma unroll
-        for (int k = 0; k < ZL; ++k)
-          if (zvalid[k]) { m |= 1 << (mylay[k] - 1); za = fmaxf(za, (float)fabs(myz[k]) * 1.0000002f); }
-        for (int o = 16; o > 0; o >>= 1) {
-          m |= __shfl_xor_sync(0xffffffffu, m, o);
-          za = fmaxf(za, __shfl_xor_sync(0xffffffffu, za, o));
-        }
-        // equally spaced slots?  D from lane 0 (slots 0,1 are always valid when nz >= 32)
-        const double D = __shfl_sync(0xffffffffu, myz[1] - myz[0], 0);
-        const double tol = 4.0 * 2.220446049250313e-16 * (double)za;
-        bool uni = __shfl_sync(0xffffffffu, (int)(zvalid[0] && zvalid[1]), 0) != 0;
-#pragma unroll
-        for (int k = 0; k + 1 < ZL; ++k)
-          if (zvalid[k] && zvalid[k + 1] && !(fabs((myz[k + 1] - myz[k]) - D) <= tol)) uni = false;
-        uni = __all_sync(0xffffffffu, uni);
-        if (lane == 0) {
-          s_misc[0] = m;
-          s_misc[1] = __float_as_int(za);
-          s_misc[2] = uni ? 1 : 0;
-          *(double *)(s_misc + 6) = D;
-        }
-      }
-    }
-    PROF_ADD(10);
-    __syncthreads();
-    PROF_ADD(1);
-    const int lay_mask = have_cur ? s_misc[0] : 1;
-    const double eta_max = fast_eta_max(P, lay_mask, (double)__int_as_float(s_misc[1]));
-    const bool zuni = s_misc[2] != 0;
-    const double Dz = *(double *)(s_misc + 6);
-    const int L0 = __ffs(lay_mask) - 1;
-    int myL[ZL];
-#pragma unroll
-    for (int k = 0; k < ZL; ++k) {
-      if (!zvalid[k]) {                 // padding slots mimic a present layer / the uniform grid
-        mylay[k] = L0 + 1;
-        myz[k] = zuni ? myz[0] + k * Dz : 0.5;
-        if (!zvalid[0]) myz[k] = 0.5;
-      }
-      myL[k] = mylay[k] - 1;
-    }
-    // slots whose lanes are not all on the layer of (slot 0, lane 0); exactly one such slot
-    // gets the cheaper "exception" loop
-    const int Lc = __shfl_sync(0xffffffffu, myL[0], 0);
-    int offmask = 0;
-#pragma unroll
-    for (int k = 0; k < ZL; ++k)
-      if (!__all_sync(0xffffffffu, myL[k] == Lc)) offmask |= 1 << k;
-    const int kx = (offmask != 0 && (offmask & (offmask - 1)) == 0) ? __ffs(offmask) - 1 : -1;
-    const bool hot_ok = (offmask & (offmask - 1)) == 0;   // at most one slot off the common layer
-    int Lx = myL[0];
-#pragma unroll
-    for (int k = 1; k < ZL; ++k) if (k == kx) Lx = myL[k];
-    // k0 of the common layer is exactly zero below/above the screen of the Hantush-type models
-    const bool k0z = (P.model == 1 || P.model == 2 || P.model == 3 || P.model == 5) && Lc != 1;
-
-    const int njobs_p = have_cur ? (np + 1) / 2 : 0;   // two Laplace parameters per p-job
-    const int njobs_d = have_prev ? (2 * prev_nzv + 31) / 32 : 0;
-    StageEnt8 *stage = s_stage + warp * 32 + half * GL;   // this half-warp's 16 staged abscissae
-    int *okv = s_ok + warp * 32 + half * GL;
-    for (;;) {
-      int job = 0;
-      if (lane == 0) job = atomicAdd(&s_misc[8], 1);
-      job = __shfl_sync(0xffffffffu, job, 0);
-      if (job >= njobs_p + njobs_d) break;
-      if (job >= njobs_p) {
-        // ---- D-job: de Hoog for 32 (z, value|derivative) pairs of the PREVIOUS item ------
-        const int idx = (job - njobs_p) * 32 + lane;
-        if (idx < 2 * prev_nzv) {
-          const int deriv = idx >= prev_nzv ? 1 : 0;
-          const int zi = idx - deriv * prev_nzv;
-          const double ptee = P.tee_mult * prev_tD;
-#ifdef UNC_SKIP_DEHOOG
-          double v = tot_prev[zi].re;
-#else
-          double v = dehoog_lane(P, tot_prev + zi, ZB, deriv != 0, prev_tD, ptee);
-#endif
-          const long long o = prev_col * (long long)J.nz + prev_z0 + zi;
-          if (deriv) J.ds[o] = v * prev_tD;  // driver.f90:228
-          else {
-            J.s[o] = v;
-            if (J.flags) J.flags[o] = flag_prev[zi] != 0ull ? 1 : 0;
-            if (J.smask) J.smask[o] = flag_prev[zi];
-            if (J.nstale && flag_prev[zi] != 0ull) atomicAdd(J.nstale, 1u);
-          }
-        }
-        __syncwarp();
-        PROF_ADD(6);
-        continue;
-      }
-      // ---- p-job: Hankel quadrature + Wynn for two Laplace parameters (one per half-warp),
-      //      128 z each.  np odd: the upper half of the last job repeats p = np-1 and stores nothing.
-      const bool pvalid = 2 * job + half < np;
-      const int pi = min(2 * job + half, np - 1);
-      int stale = 0;
-      const cplx pp = T.p[pi], aux = T.aux[pi], aux2 = T.aux2[pi];
-      // areas[k][0] = tanh-sinh part (finint), areas[k][1..nacc] = Gauss-Lobatto interval areas:
-      // one thread-local array instead of a second register set for the finite part
-      cplx areas[ZL][UNC_MAX_NACC + 1];
-      cplx acc[ZL];
-#pragma unroll
-      for (int k = 0; k < ZL; ++k) { acc[k] = mk(0.0, 0.0); areas[k][0] = mk(0.0, 0.0); }
-      int seg = 0;
-      int next_b = N;
-      // Wynn only uses the areas before the first non-finite one (integration.f90:140-160) and
-      // driver.f90:209 only asks whether SOME area is finite and non-zero.  Once that is settled
-      // for every z of the warp (dead: a non-finite area seen; anyf: a finite non-zero one seen)
-      // the remaining, ever more expensive, overflowing abscissae cannot change the result.
-      const cplx lt_chk = T.lt[pi];
-      const bool lt_ok = is_finite_fastc(lt_chk) && (lt_chk.re != 0.0 || lt_chk.im != 0.0);
-      int dead = 0, anyf = 0;
-      bool done = false;
-      // (measured: starting half of the warps with a half chunk to de-synchronise the
-      // ap_terms / hot-loop phases of the warps sharing a scheduler is 2% SLOWER)
-      for (int base = 0; base < NA && !done; base += GL) {
-        int ok = 1;
-        {
-          const int idx = base + hl;
-          if (idx < NA)
-            ok = ap_terms_stage8(P, pp, aux, aux2, s_a2[idx], s_wj[idx], lay_mask, eta_max, zuni, Dz, kx,
-                                 &stage[hl]);
-          okv[hl] = ok;
-        }
-        const bool all_ok = __all_sync(0xffffffffu, ok);
-        __syncwarp();
-        PROF_ADD(2);
-        const int cnt = min(GL, NA - base);
-        int j = 0;
-        while (j < cnt) {
-          const int jend = min(cnt, next_b - base);
-          if (all_ok && zuni && hot_ok) {
-            // hot loop over the whole chunk (segment ends are handled inside the call)
-            const int seg0 = seg;
-#ifndef UNC_SKIP_HOT
-#define UNC_H8(KXV, KZV) seg = hot8_chunk<KXV, KZV>(stage, cnt, myz[0], Lc, Lx, acc, &areas[0][0], seg, next_b - base, NA - base, G)
-            if (kx < 0) {
-              if (k0z) UNC_H8(-1, true); else UNC_H8(-1, false);
-            } else if (k0z) {
-              switch (kx) {
-                case 0: UNC_H8(0, true); break;
-                case 1: UNC_H8(1, true); break;
-                case 2: UNC_H8(2, true); break;
-                case 3: UNC_H8(3, true); break;
-                case 4: UNC_H8(4, true); break;
-                case 5: UNC_H8(5, true); break;
-                case 6: UNC_H8(6, true); break;
-                default: UNC_H8(7, true); break;
-              }
-            } else {
-              switch (kx) {
-                case 0: UNC_H8(0, false); break;
-                case 1: UNC_H8(1, false); break;
-                case 2: UNC_H8(2, false); break;
-                case 3: UNC_H8(3, false); break;
-                case 4: UNC_H8(4, false); break;
-                case 5: UNC_H8(5, false); break;
-                case 6: UNC_H8(6, false); break;
-                default: UNC_H8(7, false); break;
-              }
-            }
-#undef UNC_H8
-#else
-            while (next_b - base <= cnt && next_b < NA) { seg += 1; next_b += G; }
-            next_b -= (seg - seg0) * G;
-#endif
-            next_b += (seg - seg0) * G;
-            j = cnt;
-            // fate of the intervals closed inside this chunk (see the comment at `dead`)
-            if (lt_ok) {
-              for (int sidx = max(seg0, 1); sidx < seg && !done; ++sidx) {
-                int cur_bad = 0;
-#pragma unroll
-                for (int k = 0; k < ZL; ++k) {
-                  const cplx a = areas[k][sidx];
-                  const bool f = is_finite_fastc(a);
-                  if (!f) cur_bad |= 1 << k;
-                  if (f && (a.re != 0.0 || a.im != 0.0)) anyf |= 1 << k;
-                }
-                dead |= cur_bad;
-                if (__all_sync(0xffffffffu, (dead & anyf) == (1 << ZL) - 1)) {
-                  const double nanv = __longlong_as_double(0x7ff8000000000000LL);
-#pragma unroll
-                  for (int k = 0; k < ZL; ++k) {
-                    for (int jj = sidx + 1; jj <= nacc; ++jj) areas[k][jj] = mk(nanv, nanv);
-                    acc[k] = mk(nanv, nanv);
-                  }
-                  seg = nacc;   // the final store below rewrites areas[nacc] with NaN
-                  done = true;
-                }
-              }
-            }
-            continue;
-          } else {
-            // rare: abscissae beyond the fast-path bound, z-lists that are not equally spaced,
-            // more than one slot off the common layer -- kept out of line (and re-reading its
-            // z from global memory) so that it does not weigh on the registers of the common path
-            slow8_run(P, T, pi, stage, okv, base, j, jend, s_wj, s_a2, J.zD + zbase, J.zLay + zbase, nzv, hl,
-                      L0, zuni, Dz, acc);
-            j = jend;
-          }
-          const bool seg_end = (base + j == next_b && next_b < NA);
-          if (seg >= 1 && lt_ok && (seg_end || !all_ok)) {
-            // at an interval end: record its fate; inside an interval that already went
-            // non-finite for everybody (only looked at after chunks with literal nodes): stop
-            int cur_bad = 0;
-#pragma unroll
-            for (int k = 0; k < ZL; ++k) {
-              const bool f = is_finite_fastc(acc[k]);
-              if (!f) cur_bad |= 1 << k;
-              if (seg_end && f && (acc[k].re != 0.0 || acc[k].im != 0.0)) anyf |= 1 << k;
-            }
-            if (seg_end) dead |= cur_bad;
-            const int settled = (dead | cur_bad) & anyf;
-            if (__all_sync(0xffffffffu, settled == (1 << ZL) - 1)) {
-              const double nanv = __longlong_as_double(0x7ff8000000000000LL);
-#pragma unroll
-              for (int k = 0; k < ZL; ++k) {
-                if (seg_end) areas[k][seg] = acc[k];
-                for (int jj = seg_end ? seg : seg - 1; jj < nacc; ++jj) areas[k][jj + 1] = mk(nanv, nanv);
-                acc[k] = mk(nanv, nanv);
-              }
-              seg = nacc;   // the final store below rewrites series[nacc-1] with NaN
-              done = true;
-              break;
-            }
-          }
-          if (seg_end) {
-#pragma unroll
-            for (int k = 0; k < ZL; ++k) {
-              areas[k][seg] = acc[k];
-              acc[k] = mk(0.0, 0.0);
-            }
-            seg += 1;
-            next_b += G;
-          }
-        }
-        __syncwarp();
-        PROF_ADD(3);
-      }
-#pragma unroll
-      for (int k = 0; k < ZL; ++k) areas[k][seg] = acc[k];
-      // lapTime, Wynn-epsilon on the interval areas, totlap = finint + infint for the 8 slots
-#ifndef UNC_WYNN_LOCALMEM
-      stale = finish8(&areas[0][0], nacc, T.lt[pi], pvalid ? tot + (size_t)pi * ZB + hl : nullptr,
-                      (cplx *)(s_stage + warp * 32) + lane);
-      __syncwarp();   // the scratch becomes the stage of the next job again
-#else
-      stale = finish8(&areas[0][0], nacc, T.lt[pi], pvalid ? tot + (size_t)pi * ZB + hl : nullptr, nullptr);
-#endif
-#pragma unroll
-      for (int k = 0; k < ZL; ++k) if (pvalid && (stale & (1 << k))) atomicOr(&flag_cur[GL * k + hl], 1ull << pi);
-      PROF_ADD(4);
-    }
-    PROF_ADD(5);
-    have_prev = have_cur;
-    prev_col = col; prev_z0 = z0; prev_nzv = nzv; prev_tD = tD;
-    buf ^= 1;
-  }
-}
-
-
 // test hook (unc_debug_cbesk01): K0, K1 of n complex arguments by the device routine
 __global__ void cbesk01_test_kernel(int n, const double *z, double *out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2114,3 +1692,5 @@ __global__ void fp64_peak_kernel(double *out, int iters) {
 }
 
 }  // namespace unc
+
+#include "grid8.cuh"
