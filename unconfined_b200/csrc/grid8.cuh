@@ -263,6 +263,7 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
           J.s[o] = v;
           if (J.flags) J.flags[o] = flag_prev[zi] != 0ull ? 1 : 0;
           if (J.smask) J.smask[o] = flag_prev[zi];
+          if (J.nstale && flag_prev[zi] != 0ull) atomicAdd(J.nstale, 1u);
         }
       }
       __syncwarp();
