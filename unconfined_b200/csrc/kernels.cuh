@@ -920,6 +920,7 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
     const int nts_rounds = P.nts_pad / 32;
     cplx *area_p = s_area_all + ((size_t)u * np + pi) * ZT * nacc;
     int jrun = 0;   // interval whose area the lanes are accumulating in run[] (uniform over the warp)
+    int jlo_next = 0;   // first interval of the current round
     // (a source of the carry post-pass only needs the Gauss-Lobatto part)
     for (int i = (fix_mode == 1) ? nts_rounds : 0; i < nts_rounds + rounds; ++i) {
       const bool ts = i < nts_rounds;
@@ -955,9 +956,13 @@ lh_point_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
         for (int k = 0; k < ZT; ++k) accT[k] = caddf(accT[k], f[k]);
       } else {
         // the (at most two, for G >= 32) intervals this round touches, in order
-        const int base = (i - nts_rounds) * 32;
-        const int j_lo = base / G, j_hi = min(base + 31, ngl - 1) / G;
-        const int myj = valid ? node / G : -1;
+        // (no integer divisions here: the first interval of a round follows from the previous round's)
+        const int base = (i - nts_rounds) * 32, last = min(base + 31, ngl - 1);
+        while (base >= (jlo_next + 1) * G) jlo_next += 1;
+        const int j_lo = jlo_next;
+        int j_hi = j_lo, myj = -1;
+        while (last >= (j_hi + 1) * G) j_hi += 1;
+        if (valid) { myj = j_lo; while (node >= (myj + 1) * G) myj += 1; }
         for (int j = j_lo; j <= j_hi; ++j) {
           if (j != jrun) {
             // interval jrun is complete: per-lane partial sums -> its area (once per interval)
