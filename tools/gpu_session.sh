@@ -15,6 +15,7 @@ ref)    timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpur
 c5b)    timeout 600 python tools/bench_c5b.py 17 3 > gpurun_out/${T}_c5b.json 2> gpurun_out/${T}_c5b.err; cat gpurun_out/${T}_c5b.json; tail -3 gpurun_out/${T}_c5b.err ;;
 variants) timeout 1500 python tools/variants.py run gpurun_out/${T}_variants.txt > gpurun_out/${T}_variants.log 2>&1; cat gpurun_out/${T}_variants.txt ;;
 ngpu)   timeout 600 python tools/bench_ngpu.py gpurun_out/${T}_strong_ngpu.json > gpurun_out/${T}_ngpu.log 2>&1; tail -12 gpurun_out/${T}_ngpu.log ;;
+parity) timeout 1500 python tools/parity_report.py --out gpurun_out/${T}_parity.txt > gpurun_out/${T}_parity.log 2>&1; tail -70 gpurun_out/${T}_parity.txt ;;
 decks)  timeout 600 python tools/bench_decks.py > gpurun_out/${T}_decks.txt 2>&1; cat gpurun_out/${T}_decks.txt ;;
 launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/${T}_ncu_launch.log 2>&1; tail -2 gpurun_out/${T}_ncu_launch.log ;;
 ncu_point) timeout 900 ncu --set full --clock-control none --import-source on -k regex:lh_point --launch-skip 1 -c 1 -o gpurun_out/${T}_point -f python tools/bench_c5b.py 15 1 > gpurun_out/${T}_ncu_point.log 2>&1; tail -2 gpurun_out/${T}_ncu_point.log ;;

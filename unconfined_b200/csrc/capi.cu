@@ -816,14 +816,6 @@ int run_host(const unc_params *prm, HostJob hj, int ngpu) {
 
 extern "C" {
 
-#ifdef UNC_PROFILE
-int unc_debug_profile(unsigned long long *out, int reset) {
-  unsigned long long z[16] = {0};
-  if (out) cudaMemcpyFromSymbol(out, unc::g_prof, sizeof z);
-  if (reset) cudaMemcpyToSymbol(unc::g_prof, z, sizeof z);
-  return 0;
-}
-#endif
 
 const char *unc_version(void) { return "unconfined_b200 0.1 (sm_100a)"; }
 const char *unc_last_error(void) { return g_err.c_str(); }
