@@ -151,6 +151,7 @@ int unc_device_info(int32_t *ngpu, double *fp64_peak_flops /* nominal: SMs*64*2*
 int unc_measure_fp64_peak(double *flops); /* DFMA-chain microbenchmark on the current device */
 int unc_kernel_launch_count(int64_t *n);  /* kernels launched by this library so far */
 int unc_shutdown(void);                   /* frees cached device buffers */
+int unc_release_stream(void *stream);     /* frees what the *_device entry points cached for this stream */
 int unc_set_carry(int32_t on);            /* default 1: see UNC_FLAG_STALE_INFINT */
 int unc_debug_cbesk01(int32_t n, const double *z /* [2n] */, double *out /* [4n]: K0, K1 */); /* test hook: device cbknu */
 int unc_debug_force_kernel(int32_t which);/* test hook: 0 auto, 1 point kernel, 2 grid kernels,

@@ -907,6 +907,24 @@ int unc_shutdown(void) {
   return UNC_OK;
 }
 
+/* frees the scratch, counters and tables the library keeps for `stream` on the current device
+ * (they are otherwise cached until unc_shutdown); synchronises the stream first */
+int unc_release_stream(void *stream) {
+  std::lock_guard<std::mutex> lk(g_mutex);
+  DeviceGuard guard;
+  if (device_count() <= 0) return UNC_OK;
+  DevCtx &c = g_ctx[g_device];
+  if (!c.init) return UNC_OK;
+  CK(cudaSetDevice(g_device));
+  cudaStream_t st = (cudaStream_t)stream;
+  auto it = c.res.find(st);
+  if (it == c.res.end()) return UNC_OK;
+  CK(cudaStreamSynchronize(st));
+  it->second.release();
+  c.res.erase(it);
+  return UNC_OK;
+}
+
 /* 1 (default): grid calls that pass ts_abscissa_scale (reference-compatible mode) also
  * reproduce the reference's stale infint (driver.f90:205-214); 0: such points get infint = 0
  * and UNC_FLAG_STALE_INFINT only, as calls with ts_abscissa_scale = NULL always do */
