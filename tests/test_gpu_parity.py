@@ -126,7 +126,7 @@ def test_scattered_points_c5b_sample():
     check_parity(sg, dg, so, do, sps, spd, what="scatter")
 
 
-@pytest.mark.parametrize("nz", [1, 2, 3, 5, 12, 33, 40])
+@pytest.mark.parametrize("nz", [1, 2, 3, 5, 12, 33, 40, 70])   # 70: the 128-z kernel with padding slots
 def test_ragged_z_counts_and_kernel_agreement(nz):
     d, pd = load_deck("cape-cod-neuman74.in")
     zD = np.linspace(0.0, 1.0, nz) if nz > 1 else np.array([0.4])
@@ -207,7 +207,7 @@ GRID_DECKS = ["theis-input.dat", "hantush-input.dat", "hantush-storage-input.dat
 
 @pytest.mark.parametrize("name", GRID_DECKS)
 def test_every_model_through_the_128z_grid_kernels(name):
-    """Models 0-6 through lh_grid8_kernel (nz >= 96): z-lists that stay in one layer, straddle
+    """Models 0-6 through lh_grid8_kernel (nz >= 64): z-lists that stay in one layer, straddle
     one layer boundary in one slot, and cross both boundaries; checked against the lanes<->z
     grid kernel and the point kernel (themselves held to the oracle on the decks above) and,
     on a sample, against the oracle with its noise envelope."""

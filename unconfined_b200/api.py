@@ -230,11 +230,11 @@ def set_carry(on):
     _ck(lib().unc_set_carry(1 if on else 0))
 
 
-_KERNELS = {None: 0, "auto": 0, "point": 1, "grid": 2, "grid2": 3}
+_KERNELS = {None: 0, "auto": 0, "point": 1, "grid": 2, "grid2": 3, "grid8": 4}
 
 
 def force_kernel(which=None):
-    """Test hook (unc_debug_force_kernel): None/'auto', 'point', 'grid', 'grid2'."""
+    """Test hook (unc_debug_force_kernel): None/'auto', 'point', 'grid', 'grid2', 'grid8'."""
     _ck(lib().unc_debug_force_kernel(_KERNELS[which]))
 
 

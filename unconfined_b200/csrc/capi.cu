@@ -331,7 +331,13 @@ struct DevCtx {
 };
 DevCtx g_ctx[16];
 std::atomic<int> g_carry{1};   // unc_set_carry
-std::atomic<int> g_force{0};   // unc_debug_force_kernel: 0 auto, 1 point, 2 grid, 3 grid (lanes<->z kernel only)
+std::atomic<int> g_force{0};   // unc_debug_force_kernel: 0 auto, 1 point, 2 grid, 3 grid (lanes<->z kernel only), 4 grid (128-z kernel from nz = 32)
+// columns of at least this many z go to the 128-z persistent kernel (its padding slots idle):
+// measured on 1024 r x nz x 2 t of C5a, lanes<->z kernel vs 128-z kernel: nz=48 31.7 vs 56.4 ms,
+// nz=64 32.7 vs 22.1, nz=80 60.5 vs 22.4, nz=96 61.7 vs 23.0 (profiles/r02_nz_crossover.txt)
+#ifndef UNC_GRID8_MIN_NZ
+#define UNC_GRID8_MIN_NZ 64
+#endif
 
 // the library switches devices internally; the caller's current device is restored on return
 struct DeviceGuard {
@@ -482,7 +488,8 @@ int launch_grid8_nw(int dev, StreamRes &r, const unc::DevParams &P, const unc::J
 
 int launch_grid(int dev, StreamRes &r, const unc::DevParams &P, const unc::Job &J, cudaStream_t st) {
   const bool small_only = g_force.load() == 3;
-  if (J.nz >= 96 && !small_only) return launch_grid8_nw<UNC_GRID8_NW>(dev, r, P, J, st);
+  if ((J.nz >= UNC_GRID8_MIN_NZ && !small_only) || (g_force.load() == 4 && J.nz >= 32))
+    return launch_grid8_nw<UNC_GRID8_NW>(dev, r, P, J, st);
   // two z per lane (64 z per CTA) halves the per-(a,p) work per point; keep one z per lane
   // for short columns and when the larger totlap tile would not fit twice per SM
   if (J.nz > 32 && P.np <= 53) return launch_grid_zl<2>(dev, P, J, st);
@@ -496,9 +503,9 @@ int launch(int dev, StreamRes &r, const unc::DevParams &P, const unc::Job &J, cu
   bool grid = J.nz >= 12;
   // a small contour grid (fewer column CTAs than SMs) is a latency problem: the point kernel
   // spreads it over nz/4 times as many CTAs (hantush-contours deck, 30 r x 20 z: 6.9 ms -> <1 ms)
-  if (grid && J.nz < 96 && J.ncol * ((J.nz + 31) / 32) < (long long)g_ctx[dev].sm_count) grid = false;
+  if (grid && J.nz < UNC_GRID8_MIN_NZ && J.ncol * ((J.nz + 31) / 32) < (long long)g_ctx[dev].sm_count) grid = false;
   if (force == 1) grid = false;
-  if (force == 2 || force == 3) grid = true;
+  if (force == 2 || force == 3 || force == 4) grid = true;
   if (grid) return launch_grid(dev, r, P, J, st);
 #ifdef UNC_BUDGET_SEQSUM
   return launch_zt<1>(dev, P, J, st);   // error-budget builds: the sequential sums exist for one z per CTA only
@@ -955,9 +962,9 @@ int unc_debug_cbesk01(int32_t n, const double *z, double *out) {
 }
 
 /* test hook: pin the kernel family (0 auto, 1 point kernel, 2 grid kernels, 3 the lanes<->z
- * grid kernel even for nz >= 96); never needed by a caller of the product */
+ * grid kernel even for nz >= 64; 4 the 128-z kernel from nz = 32); never needed by a caller of the product */
 int unc_debug_force_kernel(int32_t which) {
-  if (which < 0 || which > 3) return fail(UNC_ERR_BAD_ARG, "which must be 0..3");
+  if (which < 0 || which > 4) return fail(UNC_ERR_BAD_ARG, "which must be 0..4");
   g_force.store(which);
   return UNC_OK;
 }
