@@ -314,9 +314,10 @@ struct StreamRes {
   std::vector<double> blob_cached;
   // carry post-pass
   DevBuf mask, slot, need, src_slot, list, src_list, fix_src, fix_val, fix_out, counts, cin;
+  DevBuf order, bins;   // cost-ordered unit list of large point sets
   void release() {
     for (DevBuf *b : {&tables, &scratch, &counter, &mask, &slot, &need, &src_slot, &list, &src_list,
-                      &fix_src, &fix_val, &fix_out, &counts, &cin})
+                      &fix_src, &fix_val, &fix_out, &counts, &cin, &order, &bins})
       b->release();
   }
 };
@@ -401,17 +402,17 @@ int launch_point(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream
   return UNC_OK;
 }
 
-// ZT z-values of one column per work unit; for ZT = 1 (scattered points, time series) a CTA takes
-// two units so that its Wynn and de Hoog phases are fuller -- when there are enough units to
-// fill the GPU that way and two such CTAs still fit an SM
+// ZT z-values of one column per work unit; for ZT = 1 (scattered points, time series) a CTA can
+// take several units so that its Wynn and de Hoog phases are fuller (UNC_POINT_PTMAX; measured
+// below: one unit per CTA is best once large point sets are cost-ordered)
 template <int ZT>
 int launch_zt(int dev, const unc::DevParams &P, const unc::Job &J, cudaStream_t st, long long nunits_fix = -1) {
   const long long ntiles = (J.nz + ZT - 1) / ZT;
   const long long nunits = nunits_fix >= 0 ? nunits_fix : J.ncol * ntiles;
   if (ZT == 1) {
 #ifndef UNC_POINT_PTMAX
-#define UNC_POINT_PTMAX 2   // C5b, ms per 2^17 points: one unit per CTA 290, two 287, four 318 (instruction-cache misses)
-#endif
+#define UNC_POINT_PTMAX 1   // C5b, ms per 2^17 points, one / two / four units per CTA: 290 / 287 / 318 in input order
+#endif                      // (instruction-cache misses), 278.5 / 281.7 / 290.2 with cost-ordered units
 #ifndef UNC_BUDGET_SEQSUM
     const int na = P.nts_pad + P.gl_rounds * 32;
     const int cta_per_sm = 16 / UNC_PWARPS;
@@ -507,6 +508,26 @@ int launch(int dev, StreamRes &r, const unc::DevParams &P, const unc::Job &J, cu
   if (force == 1) grid = false;
   if (force == 2 || force == 3 || force == 4) grid = true;
   if (grid) return launch_grid(dev, r, P, J, st);
+#ifndef UNC_NO_COST_ORDER
+  // large scattered point sets: most expensive (smallest rD) first, see carry.cuh
+  if (J.zstride == 1 && J.nz == 1 && J.fix_mode == 0 && J.ncol >= 16384 && J.ncol < 2147483647LL && force == 0) {
+    int rc = r.order.ensure((size_t)J.ncol * sizeof(int));
+    if (rc) return rc;
+    if ((rc = r.bins.ensure(128 * sizeof(unsigned int)))) return rc;
+    unsigned int *bins = (unsigned int *)r.bins.ptr;
+    const unsigned nb = (unsigned)((J.ncol + 255) / 256);
+    CK(cudaMemsetAsync(bins, 0, 128 * sizeof(unsigned int), st));
+    unc::cost_hist_kernel<<<nb, 256, 0, st>>>(J.rD, J.ncol, bins);
+    unc::cost_scan_kernel<<<1, 32, 0, st>>>(bins);
+    unc::cost_scatter_kernel<<<nb, 256, 0, st>>>(J.rD, J.ncol, bins, (int *)r.order.ptr);
+    g_launches += 3;
+    unc::Job Jo = J;
+    Jo.fix_mode = 3;
+    Jo.fix_n = J.ncol;
+    Jo.fix_list = (const int *)r.order.ptr;
+    return launch_zt<1>(dev, P, Jo, st, J.ncol);
+  }
+#endif
 #ifdef UNC_BUDGET_SEQSUM
   return launch_zt<1>(dev, P, J, st);   // error-budget builds: the sequential sums exist for one z per CTA only
 #endif

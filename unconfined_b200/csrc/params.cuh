@@ -44,7 +44,8 @@ struct Job {
   unsigned long long *smask;  // per point, or NULL: bit p set = infint(p,z) was stale (driver.f90:209)
   unsigned int *nstale;       // or NULL: incremented once per point with a non-zero mask
   // carry post-pass (lh_point_kernel<1> only; capi.cu carry_postpass): CTA e works on point fix_list[e]
-  int fix_mode;               // 0 normal; 1 source: Wynn result of the p in need[] -> fix_val;
+  int fix_mode;               // 0 normal; 3 normal, units taken in the order of fix_list (cost-ordered points);
+                              // 1 source: Wynn result of the p in need[] -> fix_val;
                               // 2 destination: stale infint(p) taken from fix_val[fix_src[e*np+p]]
   long long fix_n;            // number of entries
   const int *fix_list;        // [entries] point index c*nz+z
