@@ -471,9 +471,8 @@ int launch_grid8_nw(int dev, StreamRes &r, const unc::DevParams &P, const unc::J
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, unc::lh_grid8_kernel<NW>, NW * 32, smem));
   if (occ < 1) occ = 1;
   const int grid = (int)std::min<long long>(nitems, (long long)c.sm_count * occ);
-  // per CTA: three totlap slots and two table slots
-  const size_t tab_bytes = (size_t)4 * P.np * sizeof(unc::cplx) + (size_t)2 * na_seq * sizeof(double);
-  int rc = r.scratch.ensure((size_t)grid * 3 * P.np * 128 * sizeof(unc::cplx) + (size_t)grid * 2 * tab_bytes);
+  // per CTA: three totlap slots, two table slots, three stale-mask slots
+  int rc = r.scratch.ensure(unc::grid8_scratch_bytes(P.np, na_seq, grid));
   if (rc) return rc;
   rc = r.counter.ensure(256);
   if (rc) return rc;

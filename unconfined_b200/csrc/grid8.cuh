@@ -13,10 +13,18 @@ struct ItemMeta {
 
 __host__ __device__ inline size_t grid8_smem_bytes(int np, int na_seq, int NW) {
   size_t b = 0;
-  b += (size_t)NW * 32 * sizeof(StageEnt8) + (size_t)NW * 32 * sizeof(int);           // per-warp stage
-  b += 3 * 128 * sizeof(unsigned long long);                                          // stale masks
+  b += (size_t)NW * 32 * sizeof(StageEnt8);                                           // per-warp stage
   b += 3 * sizeof(ItemMeta) + 64;                                                     // descriptors, sync words
   return (b + 15) & ~(size_t)15;
+}
+
+// global scratch of one CTA: three totlap slots, two table slots, three stale-mask slots
+__host__ __device__ inline size_t grid8_tab_bytes(int np, int na_seq) {
+  return (size_t)4 * np * sizeof(cplx) + (size_t)2 * na_seq * sizeof(double);
+}
+__host__ __device__ inline size_t grid8_scratch_bytes(int np, int na_seq, int grid) {
+  return (size_t)grid * ((size_t)3 * np * 128 * sizeof(cplx) + 2 * grid8_tab_bytes(np, na_seq) +
+                         3 * 128 * sizeof(unsigned long long));
 }
 
 #ifndef UNC_GRID8_NW
@@ -81,7 +89,7 @@ __device__ __noinline__ void grid8_tjob(const DevParams &P, const Job &J, int kn
       const double arg = P.j0z[sv - 1] / rD;                      // driver.f90:120
       const double tscale = J.ts_scale ? J.ts_scale[col] : arg;  // driver.f90:121-126
       const long long zbase = (J.zstride ? col * (long long)J.nz : 0) + z0;
-      for (int i = lane; i < ZB; i += 32) s_flag[ms * 128 + i] = 0ull;
+      for (int i = lane; i < ZB; i += 32) __stcg(&s_flag[ms * 128 + i], 0ull);
       PTab T;
       double *a2, *wj;
       grid8_tables(tabs, ts, np, na_seq, T, a2, wj);
@@ -191,12 +199,14 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
 
   // the items' tables (p, lapTime, a^2, weights: 15 KB, read once per (a,p)) live in a global
   // scratch slot of the CTA (L1/L2-resident), two items deep: shared memory is left to the stage
-  const size_t tab_bytes = (size_t)4 * np * sizeof(cplx) + (size_t)2 * na_seq * sizeof(double);
+  const size_t tab_bytes = grid8_tab_bytes(np, na_seq);
   unsigned char *tabs = (unsigned char *)(g_tot + (size_t)gridDim.x * 3 * np * ZB) + (size_t)blockIdx.x * 2 * tab_bytes;
+  // stale masks (one 64-bit mask of p per z, three items deep): rarely touched, kept in the CTA's
+  // global scratch behind the tables (written with atomics, read with L2 loads)
+  unsigned long long *s_flag = (unsigned long long *)((unsigned char *)(g_tot + (size_t)gridDim.x * 3 * np * ZB) +
+                                                      (size_t)gridDim.x * 2 * tab_bytes) + (size_t)blockIdx.x * 3 * 128;
   unsigned char *sp = smem_raw;
-  StageEnt8 *s_stage = (StageEnt8 *)sp; sp += (size_t)NW * 32 * sizeof(StageEnt8);
-  int *s_ok = (int *)sp; sp += (size_t)NW * 32 * sizeof(int);
-  unsigned long long *s_flag = (unsigned long long *)sp; sp += 3 * 128 * sizeof(unsigned long long);
+  cplx *s_stage = (cplx *)sp; sp += (size_t)NW * 32 * sizeof(StageEnt8);   // [warp][st8_idx(field, abscissa, half)]
   ItemMeta *s_meta = (ItemMeta *)sp; sp += 3 * sizeof(ItemMeta);
   volatile int *s_sync = (volatile int *)sp;
   // s_sync: [0] next job, [1..3] ready (round + 1 of the descriptor in slot r%3), [4..5] p-jobs done per
@@ -209,8 +219,7 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
   if (tid < 3) s_meta[tid].valid = 0;
   __syncthreads();
 
-  StageEnt8 *stage = s_stage + warp * 32 + half * GL;   // this half-warp's 16 staged abscissae
-  int *okv = s_ok + warp * 32 + half * GL;
+  cplx *stage = s_stage + (size_t)warp * 32 * ST8_NF + st8_idx(0, 0, half);   // field 0 of this half-warp's abscissa 0
 
   if (warp == 0) grid8_tjob<ZL, ZB, GL, NDMAX>(P, J, 0, nitems, nzb, np2, tabs, s_flag, s_meta, s_sync, g_counter, lane);
   __syncthreads();
@@ -251,6 +260,7 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       if (idx < 2 * pm.nzv) {
         const int deriv = idx >= pm.nzv ? 1 : 0;
         const int zi = idx - deriv * pm.nzv;
+        const unsigned long long fl = __ldcg(&flag_prev[zi]);
         const double ptee = P.tee_mult * pm.tD;
 #ifdef UNC_SKIP_DEHOOG
         double v = tot_prev[zi].re;
@@ -261,9 +271,9 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
         if (deriv) J.ds[o] = v * pm.tD;  // driver.f90:228
         else {
           J.s[o] = v;
-          if (J.flags) J.flags[o] = flag_prev[zi] != 0ull ? 1 : 0;
-          if (J.smask) J.smask[o] = flag_prev[zi];
-          if (J.nstale && flag_prev[zi] != 0ull) atomicAdd(J.nstale, 1u);
+          if (J.flags) J.flags[o] = fl != 0ull ? 1 : 0;
+          if (J.smask) J.smask[o] = fl;
+          if (J.nstale && fl != 0ull) atomicAdd(J.nstale, 1u);
         }
       }
       __syncwarp();
@@ -286,7 +296,7 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
     const long long zbase = (J.zstride ? im.col * (long long)J.nz : 0) + im.z0;
     const int L0 = __ffs(lay_mask) - 1;
     double z_first;
-    int Lc, kx, Lx;
+    int Lc, kx, Lx, Lb = 0;
     bool hot_ok, k0z;
     {
       double myz[ZL];
@@ -318,6 +328,17 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       Lx = myL[0];
 #pragma unroll
       for (int kq = 1; kq < ZL; ++kq) if (kq == kx) Lx = myL[kq];
+#if UNC_HOT_XB
+      // ... whose lanes off the common layer all lie on ONE other layer Lb (padding lanes, whose
+      // results are dropped, join the common layer)
+      Lb = Lc;
+      if (kx >= 0) {
+        if (!(hl + GL * kx < nzv)) Lx = Lc;
+        const unsigned offl = __ballot_sync(0xffffffffu, Lx != Lc);
+        if (offl) Lb = __shfl_sync(0xffffffffu, Lx, __ffs(offl) - 1);
+        if (!__all_sync(0xffffffffu, Lx == Lc || Lx == Lb)) hot_ok = false;
+      }
+#endif
       // k0 of the common layer is exactly zero below/above the screen of the Hantush-type models
       k0z = (P.model == 1 || P.model == 2 || P.model == 3 || P.model == 5) && Lc != 1;
     }
@@ -346,11 +367,11 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       {
         const int idx = base + hl;
         if (idx < NA)
-          ok = ap_terms_stage8(P, pp, aux, aux2, s_a2[idx], s_wj[idx], lay_mask, eta_max, zuni, Dz, kx,
-                               &stage[hl]);
-        okv[hl] = ok;
+          ok = ap_terms_stage8(P, pp, aux, aux2, s_a2[idx], s_wj[idx], lay_mask, eta_max, zuni, Dz, kx, Lb,
+                               stage + hl * ST8_JSTEP);
       }
-      const bool all_ok = __all_sync(0xffffffffu, ok);
+      const unsigned okball = __ballot_sync(0xffffffffu, ok);
+      const bool all_ok = okball == 0xffffffffu;
       __syncwarp();
       const int cnt = min(GL, NA - base);
       int jj = 0;
@@ -422,7 +443,7 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
           // rare: abscissae beyond the fast-path bound, z-lists that are not equally spaced,
           // more than one slot off the common layer -- kept out of line (and re-reading its
           // z from global memory) so that it does not weigh on the registers of the common path
-          slow8_run(P, T, pi, stage, okv, base, jj, jend, s_wj, s_a2, J.zD + zbase, J.zLay + zbase, nzv, hl,
+          slow8_run(P, T, pi, stage, (okball >> (half * GL)) & 0xffffu, base, jj, jend, s_wj, s_a2, J.zD + zbase, J.zLay + zbase, nzv, hl,
                     L0, zuni, Dz, acc);
           jj = jend;
         }
@@ -469,7 +490,7 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
     // lapTime, Wynn-epsilon on the interval areas, totlap = finint + infint for the 8 slots
 #ifndef UNC_WYNN_LOCALMEM
     stale = finish8(&areas[0][0], nacc, T.lt[pi], pvalid ? tot + (size_t)pi * ZB + hl : nullptr,
-                    (cplx *)(s_stage + warp * 32) + lane);
+                    s_stage + (size_t)warp * 32 * ST8_NF + lane);
     __syncwarp();   // the scratch becomes the stage of the next job again
 #else
     stale = finish8(&areas[0][0], nacc, T.lt[pi], pvalid ? tot + (size_t)pi * ZB + hl : nullptr, nullptr);

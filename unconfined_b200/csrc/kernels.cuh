@@ -1394,30 +1394,90 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
 
 // ---------------------------------------------------------------------------
 // Eight z-slots per lane, two Laplace parameters per warp (lh_grid8_kernel below).
-struct StageEnt8 {
+#ifndef UNC_HOT_E2
+#define UNC_HOT_E2 1   // slot values from two-step anchors (see eval8_scaled); 0 = one-step recurrences
+#endif
+#ifndef UNC_HOT_XB
+#define UNC_HOT_XB 1   // exception slot from pre-scaled other-layer coefficients (see eval8_scaled)
+#endif
+#ifndef UNC_SPX_POW
+#define UNC_SPX_POW 1  // exp(+-eta*D*kx) as a product of exp(+-eta*D*{1,2,4}) instead of a fourth exponential
+#endif
+#if UNC_HOT_XB && !UNC_HOT_E2
+#error "UNC_HOT_XB needs UNC_HOT_E2"
+#endif
+struct StageEnt8 {   // register-side image of one staged abscissa; see st8_idx for the shared-memory layout
   cplx eta;
   Coef co[3];
   cplx sp, sm;    // exp(+-eta*D), D = z spacing between a lane's slots (16 grid steps)
-  cplx spx, smx;  // exp(+-eta*D*kx): straight to the one slot with lane-dependent layers
+  // UNC_HOT_XB: cp, cm of the exception slot's OTHER layer times exp(+-eta*D*kx);
+  // otherwise exp(+-eta*D*kx) itself: straight from slot 0 to the one slot with lane-dependent layers
+  cplx spx, smx;
+#if UNC_HOT_E2
+  cplx sp2, sm2;  // exp(+-2*eta*D)
+#endif
 };
+// A warp's stage in shared memory: 32 entries (16 abscissae x the warp's two Laplace parameters) of
+// ST8_NF complex fields, FIELD-MAJOR: field f of abscissa j of half-warp h at complex index
+// f*32 + 2*j + h.  The 32 lanes of the producer (lane <-> entry) then store 512 contiguous bytes per
+// field, and the two half-warps of the consumer read one 32-byte segment -- with entry-major
+// 256-byte entries every lane of a store hit the same banks (measured: 95.3 instead of 90.5
+// ms/step on C5a in spite of 13 % fewer FP64 instructions in the hot loop).
+#ifndef UNC_STAGE_SOA
+#define UNC_STAGE_SOA 1
+#endif
+constexpr int ST8_NF = (int)(sizeof(StageEnt8) / sizeof(cplx));
+static_assert(ST8_NF == (UNC_HOT_E2 ? 16 : 14) && sizeof(Coef) == 3 * sizeof(cplx), "stage field numbering");
+enum { ST8_ETA = 0, ST8_CO = 1, ST8_SP = 10, ST8_SM = 11, ST8_SPX = 12, ST8_SMX = 13, ST8_SP2 = 14, ST8_SM2 = 15 };
+__host__ __device__ __forceinline__ int st8_idx(int f, int j, int h) {
+#if UNC_STAGE_SOA
+  return f * 32 + 2 * j + h;
+#else
+  return (h * 16 + j) * ST8_NF + f;
+#endif
+}
+// complex-index step from abscissa j to j+1 and from field f to f+1
+#if UNC_STAGE_SOA
+#define ST8_JSTEP 2
+#define ST8_FSTEP 32
+#else
+#define ST8_JSTEP ST8_NF
+#define ST8_FSTEP 1
+#endif
 
 // One abscissa for the eight slots of a lane.  The slot values of the common-layer slots are
-// advanced ALREADY SCALED by the coefficients, P_k = cp e^{eta z_k}, M_k = cm e^{-eta z_k}
-// (P_{k+1} = P_k e^{eta D}, M_{k+1} = M_k e^{-eta D}: two first-order recurrences, each
-// stable in its own direction), so a slot costs 2 complex multiplies + 2 complex adds
-// instead of 2 multiplies + 8 FMA.  Slot KX (if >= 0) has lane-dependent layers: its
-// exponentials come from slot 0 in one step (spx, smx) and take the per-lane cx.
+// advanced ALREADY SCALED by the coefficients, P_k = cp e^{eta z_k}, M_k = cm e^{-eta z_k}.
+// Anchors at the even slots advance by exp(+-2 eta D) (two first-order recurrences, each stable
+// in its own direction); an odd slot is its anchor times exp(+-eta D), fused into the
+// accumulation: acc += P*E is four FMA, where advancing P and adding it are four multiply/FMA
+// plus two adds -- 36 instead of 44 FP64 instructions per direction for eight slots, and
+// dependent chains of three instead of seven multiplies.  (UNC_HOT_E2 = 0: every slot advanced
+// from its neighbour.)
+// Slot KX (if >= 0) has lane-dependent layers.  Lanes on the common layer (Lx == L) treat it like
+// any other slot.  The other lanes all lie on ONE other layer (the caller checks that); the stage
+// holds that layer's cp, cm already multiplied by exp(+-eta D KX), so their value is
+// k0' + spx*E0 + smx*E0' from the unscaled start exponentials.  Both kinds run the same eight
+// FMA on lane-selected operands.  (UNC_HOT_XB = 0: exponentials of slot KX from slot 0 in one
+// step, then the per-lane layer's coefficients: eight instructions more.)
 // K0Z: k0 of the common layer is exactly zero.
 template <int KX, bool K0Z>
-__device__ __forceinline__ void eval8_scaled(const StageEnt8 &e, const Coef &c, const Coef &cx, double z0,
-                                             cplx *acc) {
+__device__ __forceinline__ void eval8_scaled(const cplx *e, int L, int Lx, double z0, cplx *acc) {
+#define ST8F(f) e[(f) * ST8_FSTEP]
   double ep, em, cc, ss, s, cs;
   int kk;
-  exp_pm_core(e.eta.re * z0, &ep, &em, &cc, &ss, &kk);
-  sincos_q(e.eta.im * z0, &s, &cs);
+  const cplx eta = ST8F(ST8_ETA);
+  Coef c;
+  c.cp = ST8F(ST8_CO + 3 * L + 1);
+  c.cm = ST8F(ST8_CO + 3 * L + 2);
+  if (!K0Z) c.k0 = ST8F(ST8_CO + 3 * L);
+  exp_pm_core(eta.re * z0, &ep, &em, &cc, &ss, &kk);
+  sincos_q(eta.im * z0, &s, &cs);
   const cplx Ep = mk(ep * cs, ep * s), Em = mk(em * cs, -(em * s));
+#if !UNC_HOT_XB
   if (KX >= 0) {
-    const cplx Ex = (KX == 0) ? Ep : cmulf(Ep, e.spx), Mx = (KX == 0) ? Em : cmulf(Em, e.smx);
+    Coef cx;
+    cx.k0 = ST8F(ST8_CO + 3 * Lx); cx.cp = ST8F(ST8_CO + 3 * Lx + 1); cx.cm = ST8F(ST8_CO + 3 * Lx + 2);
+    const cplx Ex = (KX == 0) ? Ep : cmulf(Ep, ST8F(ST8_SPX)), Mx = (KX == 0) ? Em : cmulf(Em, ST8F(ST8_SMX));
     double fr = fma(cx.cp.re, Ex.re, cx.k0.re);
     fr = fma(-cx.cp.im, Ex.im, fr);
     fr = fma(cx.cm.re, Mx.re, fr);
@@ -1428,7 +1488,61 @@ __device__ __forceinline__ void eval8_scaled(const StageEnt8 &e, const Coef &c, 
     fi = fma(cx.cm.im, Mx.re, fi);
     acc[KX < 0 ? 0 : KX] = mk(acc[KX < 0 ? 0 : KX].re + fr, acc[KX < 0 ? 0 : KX].im + fi);
   }
+#endif
   cplx Pk = cmulf(c.cp, Ep), Mk = cmulf(c.cm, Em);
+#if UNC_HOT_E2
+  const cplx e1p = ST8F(ST8_SP), e1m = ST8F(ST8_SM), e2p = ST8F(ST8_SP2), e2m = ST8F(ST8_SM2);
+#if UNC_HOT_XB
+  const bool isB = (KX >= 0) && Lx != L;
+#endif
+#pragma unroll
+  for (int k = 0; k < 8; k += 2) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = k + h;
+      if (q != KX) {
+        if (h == 0) {
+          double fr = Pk.re + Mk.re, fi = Pk.im + Mk.im;
+          if (!K0Z) { fr += c.k0.re; fi += c.k0.im; }
+          acc[q] = mk(acc[q].re + fr, acc[q].im + fi);
+        } else {
+          double fr = K0Z ? acc[q].re : acc[q].re + c.k0.re;
+          double fi = K0Z ? acc[q].im : acc[q].im + c.k0.im;
+          fr = fma(Pk.re, e1p.re, fr);
+          fr = fma(-Pk.im, e1p.im, fr);
+          fr = fma(Mk.re, e1m.re, fr);
+          fr = fma(-Mk.im, e1m.im, fr);
+          fi = fma(Pk.re, e1p.im, fi);
+          fi = fma(Pk.im, e1p.re, fi);
+          fi = fma(Mk.re, e1m.im, fi);
+          fi = fma(Mk.im, e1m.re, fi);
+          acc[q] = mk(fr, fi);
+        }
+      }
+#if UNC_HOT_XB
+      else {
+        // common-layer lanes: anchor (times exp(+-eta D) at an odd slot); the others: start
+        // exponentials times the pre-scaled coefficients of their layer
+        const cplx one = mk(1.0, 0.0);
+        const cplx k0x = ST8F(ST8_CO + 3 * Lx);
+        const cplx X1 = isB ? Ep : Pk, X2 = isB ? Em : Mk;
+        const cplx Y1 = isB ? ST8F(ST8_SPX) : (h == 0 ? one : e1p), Y2 = isB ? ST8F(ST8_SMX) : (h == 0 ? one : e1m);
+        double fr = acc[q].re + k0x.re, fi = acc[q].im + k0x.im;
+        fr = fma(X1.re, Y1.re, fr);
+        fr = fma(-X1.im, Y1.im, fr);
+        fr = fma(X2.re, Y2.re, fr);
+        fr = fma(-X2.im, Y2.im, fr);
+        fi = fma(X1.re, Y1.im, fi);
+        fi = fma(X1.im, Y1.re, fi);
+        fi = fma(X2.re, Y2.im, fi);
+        fi = fma(X2.im, Y2.re, fi);
+        acc[q] = mk(fr, fi);
+      }
+#endif
+    }
+    if (k < 6) { Pk = cmulf(Pk, e2p); Mk = cmulf(Mk, e2m); }
+  }
+#else
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     if (k != KX) {
@@ -1436,28 +1550,10 @@ __device__ __forceinline__ void eval8_scaled(const StageEnt8 &e, const Coef &c, 
       if (!K0Z) { fr += c.k0.re; fi += c.k0.im; }
       acc[k] = mk(acc[k].re + fr, acc[k].im + fi);
     }
-    if (k < 7 && !(KX == 7 && k == 6)) { Pk = cmulf(Pk, e.sp); Mk = cmulf(Mk, e.sm); }
+    if (k < 7 && !(KX == 7 && k == 6)) { Pk = cmulf(Pk, ST8F(ST8_SP)); Mk = cmulf(Mk, ST8F(ST8_SM)); }
   }
-}
-
-template <int KX, bool K0Z>
-__device__ __noinline__ void hot8_run(const StageEnt8 *stage, int j, int jend, double z0, int L, int Lx,
-                                      cplx *acc_io) {
-  cplx acc[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = acc_io[k];
-  for (; j < jend; ++j) {
-    const StageEnt8 &e = stage[j];
-    const Coef c = e.co[L];
-    if (KX >= 0) {
-      const Coef cx = e.co[Lx];
-      eval8_scaled<KX, K0Z>(e, c, cx, z0, acc);
-    } else {
-      eval8_scaled<KX, K0Z>(e, c, c, z0, acc);
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) acc_io[k] = acc[k];
+#endif
+#undef ST8F
 }
 
 // A whole staged chunk in one call, segment ends included: when the abscissa that closes a
@@ -1468,21 +1564,14 @@ __device__ __noinline__ void hot8_run(const StageEnt8 *stage, int j, int jend, d
 // instead of one per segment piece: the per-call cost (eight accumulators through local memory,
 // pipeline fill and drain) is paid 44 instead of ~60 times per job.
 template <int KX, bool K0Z>
-__device__ __noinline__ int hot8_chunk(const StageEnt8 *stage, int cnt, double z0, int L, int Lx,
+__device__ __noinline__ int hot8_chunk(const cplx *stage /* field 0 of the half-warp's abscissa 0 */, int cnt, double z0, int L, int Lx,
                                        cplx *acc_io, cplx *areas, int seg, int seg_rel, int lim_rel, int G) {
   constexpr int AST = UNC_MAX_NACC + 1;
   cplx acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = acc_io[k];
   for (int j = 0; j < cnt; ++j) {
-    const StageEnt8 &e = stage[j];
-    const Coef c = e.co[L];
-    if (KX >= 0) {
-      const Coef cx = e.co[Lx];
-      eval8_scaled<KX, K0Z>(e, c, cx, z0, acc);
-    } else {
-      eval8_scaled<KX, K0Z>(e, c, c, z0, acc);
-    }
+    eval8_scaled<KX, K0Z>(stage + j * ST8_JSTEP, L, Lx, z0, acc);
     if (j + 1 == seg_rel && seg_rel < lim_rel) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) { areas[k * AST + seg] = acc[k]; acc[k] = mk(0.0, 0.0); }
@@ -1496,26 +1585,66 @@ __device__ __noinline__ int hot8_chunk(const StageEnt8 *stage, int cnt, double z
 }
 
 
-// The same for the eight-slot kernel: also exp(+-eta*Dz*kx) for the exception slot kx (>= 1).
+// The same for the eight-slot kernel: also exp(+-eta*Dz), its square, and for the exception slot
+// kx (>= 0; other layer Lb) exp(+-eta*Dz*kx) -- as a product of the powers 1, 2, 4 of exp(+-eta*Dz)
+// (relative error a few ulp on top of kx times that of the factor, which is what the slot
+// recurrences carry anyway) -- times that layer's cp, cm.
 template <int MODEL>
 __device__ __noinline__ int ap_terms_stage8_t(const DevParams &P, cplx p, cplx aux, cplx aux2, double a2,
                                               double w, int lay_mask, double eta_max, bool zuni,
-                                              double Dz, int kx, StageEnt8 *out) {
+                                              double Dz, int kx, int Lb, cplx *out /* field 0 of this lane's entry */) {
   StageEnt8 e;
   const bool ok = ap_terms_fast_t<MODEL>(P, p, aux, aux2, a2, w, lay_mask, eta_max, &e.eta, e.co);
   e.sp = e.sm = e.spx = e.smx = mk(1.0, 0.0);
+#if UNC_HOT_E2
+  e.sp2 = e.sm2 = mk(1.0, 0.0);
+#endif
   if (zuni && ok) {
     const cbundle S = cexp_bundle(e.eta.re * Dz, e.eta.im * Dz);
     e.sp = S.ep;
     e.sm = S.em;
+#if UNC_HOT_E2
+    e.sp2 = cmulf(S.ep, S.ep);
+    e.sm2 = cmulf(S.em, S.em);
+#endif
+#if UNC_SPX_POW && UNC_HOT_E2
+    if (kx >= 1) {
+      cplx xp = mk(1.0, 0.0), xm = mk(1.0, 0.0);
+      if (kx & 1) { xp = S.ep; xm = S.em; }
+      if (kx & 2) {
+        xp = (kx & 1) ? cmulf(xp, e.sp2) : e.sp2;
+        xm = (kx & 1) ? cmulf(xm, e.sm2) : e.sm2;
+      }
+      if (kx & 4) {
+        const cplx p4 = cmulf(e.sp2, e.sp2), m4 = cmulf(e.sm2, e.sm2);
+        xp = (kx & 3) ? cmulf(xp, p4) : p4;
+        xm = (kx & 3) ? cmulf(xm, m4) : m4;
+      }
+      e.spx = xp;
+      e.smx = xm;
+    }
+#else
     if (kx >= 1) {
       const double Dx = Dz * (double)kx;
       const cbundle X = cexp_bundle(e.eta.re * Dx, e.eta.im * Dx);
       e.spx = X.ep;
       e.smx = X.em;
     }
+#endif
   }
-  *out = e;
+  {
+    const cplx *src = (const cplx *)&e;
+#pragma unroll
+    for (int f = 0; f < ST8_NF; ++f) out[f * ST8_FSTEP] = src[f];
+  }
+#if UNC_HOT_XB
+  if (zuni && ok && kx >= 0) {
+    // this layer's cp, cm read back from the stage: no dynamic indexing of the local copy
+    const cplx bcp = out[(ST8_CO + 3 * Lb + 1) * ST8_FSTEP], bcm = out[(ST8_CO + 3 * Lb + 2) * ST8_FSTEP];
+    out[ST8_SPX * ST8_FSTEP] = cmulf(bcp, e.spx);
+    out[ST8_SMX * ST8_FSTEP] = cmulf(bcm, e.smx);
+  }
+#endif
   return ok ? 1 : 0;
 }
 
@@ -1613,10 +1742,10 @@ __device__ __noinline__ int finish8(cplx *areas, int nacc, cplx lt, cplx *out, c
 }
 
 // Exact per-slot evaluation of staged abscissae j..jend-1 for the eight z of a lane: the fast
-// closed form with one exponential per slot where the per-(a,p) terms exist (okv), the literal
+// closed form with one exponential per slot where the per-(a,p) terms exist (bit j of okbits), the literal
 // path otherwise.  z, layers and the padding-slot rules are rebuilt exactly as in the kernel.
-__device__ __noinline__ void slow8_run(const DevParams &P, const PTab &T, int pi, const StageEnt8 *stage,
-                                       const int *okv, int base, int j, int jend, const double *s_wj,
+__device__ __noinline__ void slow8_run(const DevParams &P, const PTab &T, int pi, const cplx *stage,
+                                       unsigned okbits, int base, int j, int jend, const double *s_wj,
                                        const double *s_a2, const double *zsrc, const int *lsrc, int nzv,
                                        int hl, int L0, bool zuni, double Dz, cplx *acc) {
   double myz[8];
@@ -1638,14 +1767,20 @@ __device__ __noinline__ void slow8_run(const DevParams &P, const PTab &T, int pi
     }
   }
   for (; j < jend; ++j) {
-    if (okv[j]) {
+    if ((okbits >> j) & 1u) {
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        acc[k] = caddf(acc[k], eval_z_fast(stage[j].eta, stage[j].co[mylay[k] - 1], myz[k]));
+      {
+        const cplx *e = stage + j * ST8_JSTEP;
+        Coef c;
+        const int fb = ST8_CO + 3 * (mylay[k] - 1);
+        c.k0 = e[fb * ST8_FSTEP]; c.cp = e[(fb + 1) * ST8_FSTEP]; c.cm = e[(fb + 2) * ST8_FSTEP];
+        acc[k] = caddf(acc[k], eval_z_fast(e[ST8_ETA * ST8_FSTEP], c, myz[k]));
+      }
     } else {
       const int id = base + j;
       const double w = s_wj[id];
-      const bool sure_nan = literal_is_nan(P, stage[j].eta);
+      const bool sure_nan = literal_is_nan(P, stage[j * ST8_JSTEP + ST8_ETA * ST8_FSTEP]);
       const double nanv = __longlong_as_double(0x7ff8000000000000LL);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -1659,18 +1794,18 @@ __device__ __noinline__ void slow8_run(const DevParams &P, const PTab &T, int pi
 
 __device__ __forceinline__ int ap_terms_stage8(const DevParams &P, cplx p, cplx aux, cplx aux2, double a2,
                                                double w, int lay_mask, double eta_max, bool zuni,
-                                               double Dz, int kx, StageEnt8 *out) {
+                                               double Dz, int kx, int Lb, cplx *out) {
 #ifdef UNC_AP_RUNTIME_MODEL
-  return ap_terms_stage8_t<-1>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, out);
+  return ap_terms_stage8_t<-1>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, Lb, out);
 #else
   switch (P.model) {   // warp-uniform
-    case 0: return ap_terms_stage8_t<0>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, out);
-    case 1: return ap_terms_stage8_t<1>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, out);
-    case 2: return ap_terms_stage8_t<2>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, out);
-    case 3: return ap_terms_stage8_t<3>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, out);
-    case 4: return ap_terms_stage8_t<4>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, out);
-    case 5: return ap_terms_stage8_t<5>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, out);
-    default: return ap_terms_stage8_t<6>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, out);
+    case 0: return ap_terms_stage8_t<0>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, Lb, out);
+    case 1: return ap_terms_stage8_t<1>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, Lb, out);
+    case 2: return ap_terms_stage8_t<2>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, Lb, out);
+    case 3: return ap_terms_stage8_t<3>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, Lb, out);
+    case 4: return ap_terms_stage8_t<4>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, Lb, out);
+    case 5: return ap_terms_stage8_t<5>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, Lb, out);
+    default: return ap_terms_stage8_t<6>(P, p, aux, aux2, a2, w, lay_mask, eta_max, zuni, Dz, kx, Lb, out);
   }
 #endif
 }
