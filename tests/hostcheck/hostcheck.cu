@@ -44,11 +44,13 @@ void hc_exp_pm(double x, double *out) {
 }
 
 // which: 0 = dispatcher used by the kernels, 1 = local-memory version, 2 = register version, 3 = blocked,
-// 4 = single-array lozenge (shared-memory version; here on a plain buffer with stride 3)
+// 4 = single-array lozenge (shared-memory version; here on a plain buffer with stride 3),
+// 5 = the same with two anti-diagonals in lockstep (the grid kernel's)
 void hc_wynn(const double *series, int n, int which, double *out) {
   unc::cplx s[UNC_MAX_NACC];
   for (int i = 0; i < n; ++i) s[i] = unc::mk(series[2 * i], series[2 * i + 1]);
   unc::cplx Dbuf[3 * UNC_MAX_NACC];
+  if (which == 5) { unc::cplx r5 = unc::wynn_loz2(s, n, Dbuf, 3); out[0] = r5.re; out[1] = r5.im; return; }
   if (which == 4) { unc::cplx r4 = unc::wynn_loz(s, n, Dbuf, 3); out[0] = r4.re; out[1] = r4.im; return; }
   unc::cplx r = which == 1 ? unc::wynn_dev(s, n) : (which == 2 ? unc::wynn_reg<12>(s, n) : (which == 3 ? unc::wynn_blk(s, n) : unc::wynn_any(s, n)));
   out[0] = r.re; out[1] = r.im;

@@ -197,17 +197,27 @@ __host__ __device__ __forceinline__ void sincos_q(double y, double *sn, double *
   *cs = UNC_HILO2D(UNC_HIINT(b) ^ sb, UNC_LOINT(b));
 }
 
+#ifndef UNC_RCP_CUBIC
+#define UNC_RCP_CUBIC 1
+#endif
 // 1/x for x in the normal range: hardware approximation (MUFU.RCP64H, ~20 bits) + two
 // Newton steps (4 DFMA) instead of the ~25-instruction IEEE division sequence; <= 1 ulp.
 __host__ __device__ __forceinline__ double rcp_fast(double x) {
 #if defined(__CUDA_ARCH__) && !defined(UNC_BUDGET_IEEE_DIV)
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#if UNC_RCP_CUBIC
+  // one third-order step: y (1 + e + e^2), e = 1 - x y <= 2^-20  ->  residual e^3 < 2^-60
+  const double e = fma(-x, y, 1.0);
+  const double t = fma(e, e, e);
+  return fma(y, t, y);
+#else
   double e = fma(-x, y, 1.0);
   y = fma(y, e, y);
   e = fma(-x, y, 1.0);
   y = fma(y, e, y);
   return y;
+#endif
 #else
   return 1.0 / x;
 #endif
@@ -262,10 +272,19 @@ struct Coef {  // f(z) = k0 + cp*exp(eta z) + cm*exp(-eta z)
 //   aux2 : model 2: p*tDb + 1
 // MODEL >= 0: the model is a compile-time constant (the other models' branches vanish from the
 // instantiation: less code, fewer live values); MODEL = -1: taken from P at run time.
-template <int MODEL>
-__host__ __device__ __forceinline__ bool ap_terms_fast_t(const DevParams &P, cplx p, cplx aux, cplx aux2,
+// The coefficients of a layer go to sink.set(L, k0, cp, cm) as soon as they are final (the
+// water-table term is formed before the layers are assembled), so that a sink that stores them
+// -- the grid kernel's shared-memory stage -- does not carry 18 doubles to the end of the function.
+struct CoefRegSink {   // the plain Coef[3] of the point kernel, the lanes<->z kernel and the host checks
+  Coef *co;
+  __host__ __device__ __forceinline__ void set(int L, cplx k0, cplx cp, cplx cm) const {
+    co[L].k0 = k0; co[L].cp = cp; co[L].cm = cm;
+  }
+};
+template <int MODEL, class Sink>
+__host__ __device__ __forceinline__ bool ap_terms_fast_s(const DevParams &P, cplx p, cplx aux, cplx aux2,
                                                 double a2, double w, int lay_mask, double eta_max,
-                                                cplx *eta_out, Coef *co /* [3], indexed by layer-1 */) {
+                                                cplx *eta_out, const Sink &sink) {
   const int model = (MODEL >= 0) ? MODEL : P.model;
   const cplx pa = mk(p.re + a2, p.im);
   const cplx zero = mk(0.0, 0.0);
@@ -273,7 +292,7 @@ __host__ __device__ __forceinline__ bool ap_terms_fast_t(const DevParams &P, cpl
     const cplx th = cscalef(crecipf(pa), 2.0 * w);  // theis :122-131
     *eta_out = zero;
 #pragma unroll
-    for (int L = 0; L < 3; ++L) { co[L].k0 = th; co[L].cp = zero; co[L].cm = zero; }
+    for (int L = 0; L < 3; ++L) sink.set(L, th, zero, zero);
     return true;
   }
   const cplx eta = csqrt_pos(cscalef(pa, 1.0 / P.kappa));
@@ -300,56 +319,53 @@ __host__ __device__ __forceinline__ bool ap_terms_fast_t(const DevParams &P, cpl
     else ud = cdivf(u, csubf(cmulf(eta, E1.sh), cmulf(u, E1.ch)));
     const cplx g = cscalef(cmulf(th, ud), 0.5);
 #pragma unroll
-    for (int L = 0; L < 3; ++L) { co[L].k0 = th; co[L].cp = g; co[L].cm = g; }
+    for (int L = 0; L < 3; ++L) sink.set(L, th, g, g);
     return true;
   }
   cplx K0;  // common prefactor of the layer functions, weight folded in
   if (model == 2) K0 = cscalef(cdivf(aux, cmulf(pa, aux2)), w / P.bD);            // uDf/bD :265-266,299
   else K0 = cscalef(crecipf(pa), 2.0 * w / ((model == 4) ? 1.0 : P.bD));          // theis/bD
-  cplx top = zero;  // udp at zD=1 (layer 3) for models 3 and 5
   if (model == 4) {
+    // water-table term (:69-92) on top = K0
+    const cplx xi = cdivf(cscalef(eta, P.alphaD), p);
+    const cplx bex = cscalef(cmulf(eta, xi), P.beta);
+    const double MAXEXP = 12.014551129705717;          // constants.f90:66
+    cplx dcp, dcm;
+    if (eta.re < MAXEXP) {
+      const cplx D = caddf(cmulf(mk(1.0 + bex.re, bex.im), E1.ch), cmulf(xi, E1.sh));
+      dcp = cscalef(cdivf(K0, D), 0.5);
+      dcm = dcp;
+    } else {
+      const cplx D = mk(1.0 + bex.re + xi.re, bex.im + xi.im);
+      dcp = cmulf(cdivf(K0, D), E1.em);
+      dcm = zero;
+    }
 #pragma unroll
-    for (int L = 0; L < 3; ++L) { co[L].k0 = K0; co[L].cp = zero; co[L].cm = zero; }
-    top = K0;
-  } else {
-    // 1/sinh(eta); for Re(eta) > 20, sinh = e^eta (1 - e^-2eta)/2 with e^-2eta < 2^-57
-    const cplx ish = (eta.re > 20.0) ? cscalef(E1.em, 2.0) : crecipf(E1.sh);
-    const double h = 0.5 * P.bD, m = 0.5 * (P.dD1 + P.lD1);
-    const bool need13 = (lay_mask & 5) || model == 3 || model == 5;
-    if (need13) {
-      const cbundle Eh = cexp_bundle(eta.re * h, eta.im * h);
-      const cbundle Em = cexp_bundle(eta.re * m, eta.im * m);
-      const cplx sK = cmulf(K0, cmulf(Eh.sh, ish));  // K0 sinh(eta h)/sinh(eta)
-      // above the screen: 2 sK cosh(eta m) cosh(eta(1-z))
-      const cplx G3 = cmulf(sK, Em.ch);              // (half of it: the 2 cancels the 1/2 of cosh)
-      co[2].k0 = zero;
-      co[2].cp = cmulf(G3, E1.em);
-      co[2].cm = cmulf(G3, E1.ep);
-      top = cscalef(G3, 2.0);                        // cosh(0) = 1
-      // below the screen: 2 sK cosh(eta(1-m)) cosh(eta z)
-      const cplx c1m = cscalef(caddf(cmulf(E1.ep, Em.em), cmulf(E1.em, Em.ep)), 0.5);
-      const cplx G1 = cmulf(sK, c1m);
-      co[0].k0 = zero;
-      co[0].cp = G1;
-      co[0].cm = G1;
-    }
-    if (lay_mask & 2) {
-      // beside the screen: K0 (1 - A cosh(eta z) - B cosh(eta(1-z)))
-      const cbundle Ed = cexp_bundle(eta.re * P.dD, eta.im * P.dD);
-      const cbundle El = cexp_bundle(eta.re * P.lD1, eta.im * P.lD1);
-      const cplx A = cmulf(Ed.sh, ish), B = cmulf(El.sh, ish);
-      co[1].k0 = K0;
-      co[1].cp = cmulf(K0, cscalef(caddf(A, cmulf(B, E1.em)), -0.5));
-      co[1].cm = cmulf(K0, cscalef(caddf(A, cmulf(B, E1.ep)), -0.5));
-    }
+    for (int L = 0; L < 3; ++L) sink.set(L, K0, csubf(zero, dcp), csubf(zero, dcm));
+    return true;
   }
+  // 1/sinh(eta); for Re(eta) > 20, sinh = e^eta (1 - e^-2eta)/2 with e^-2eta < 2^-57
+  const cplx ish = (eta.re > 20.0) ? cscalef(E1.em, 2.0) : crecipf(E1.sh);
+  const double h = 0.5 * P.bD, m = 0.5 * (P.dD1 + P.lD1);
+  const bool need13 = (lay_mask & 5) || model == 3 || model == 5;
+  cplx G3 = zero, sK = zero;
+  cbundle Em;
+  Em.ep = Em.em = Em.ch = Em.sh = zero;
+  if (need13) {
+    const cbundle Eh = cexp_bundle(eta.re * h, eta.im * h);
+    Em = cexp_bundle(eta.re * m, eta.im * m);
+    sK = cmulf(K0, cmulf(Eh.sh, ish));   // K0 sinh(eta h)/sinh(eta)
+    // above the screen: 2 sK cosh(eta m) cosh(eta(1-z))
+    G3 = cmulf(sK, Em.ch);               // (half of it: the 2 cancels the 1/2 of cosh)
+  }
+  cplx dcp = zero, dcm = zero;
   if (model >= 3) {
-    // water-table term, :69-92
+    // water-table term, :69-92, on top = udp at zD=1 (layer 3) = 2 G3 (cosh(0) = 1)
+    const cplx top = cscalef(G3, 2.0);
     cplx xi = cdivf(cscalef(eta, P.alphaD), p);
     if (model == 3) xi = cdivf(cscalef(xi, (double)P.moench_M), aux);
     const cplx bex = cscalef(cmulf(eta, xi), P.beta);  // beta*eta*xi
     const double MAXEXP = 12.014551129705717;          // constants.f90:66
-    cplx dcp, dcm;
     if (eta.re < MAXEXP) {
       const cplx D = caddf(cmulf(mk(1.0 + bex.re, bex.im), E1.ch), cmulf(xi, E1.sh));
       dcp = cscalef(cdivf(top, D), 0.5);
@@ -359,13 +375,34 @@ __host__ __device__ __forceinline__ bool ap_terms_fast_t(const DevParams &P, cpl
       dcp = cmulf(cdivf(top, D), E1.em);
       dcm = zero;
     }
-#pragma unroll
-    for (int L = 0; L < 3; ++L) {
-      co[L].cp = csubf(co[L].cp, dcp);
-      co[L].cm = csubf(co[L].cm, dcm);
-    }
+  }
+  const bool wt = model >= 3;
+  if (need13) {
+    sink.set(2, zero, wt ? csubf(cmulf(G3, E1.em), dcp) : cmulf(G3, E1.em),
+             wt ? csubf(cmulf(G3, E1.ep), dcm) : cmulf(G3, E1.ep));
+    // below the screen: 2 sK cosh(eta(1-m)) cosh(eta z)
+    const cplx c1m = cscalef(caddf(cmulf(E1.ep, Em.em), cmulf(E1.em, Em.ep)), 0.5);
+    const cplx G1 = cmulf(sK, c1m);
+    sink.set(0, zero, wt ? csubf(G1, dcp) : G1, wt ? csubf(G1, dcm) : G1);
+  }
+  if (lay_mask & 2) {
+    // beside the screen: K0 (1 - A cosh(eta z) - B cosh(eta(1-z)))
+    const cbundle Ed = cexp_bundle(eta.re * P.dD, eta.im * P.dD);
+    const cbundle El = cexp_bundle(eta.re * P.lD1, eta.im * P.lD1);
+    const cplx A = cmulf(Ed.sh, ish), B = cmulf(El.sh, ish);
+    const cplx cp1 = cmulf(K0, cscalef(caddf(A, cmulf(B, E1.em)), -0.5));
+    const cplx cm1 = cmulf(K0, cscalef(caddf(A, cmulf(B, E1.ep)), -0.5));
+    sink.set(1, K0, wt ? csubf(cp1, dcp) : cp1, wt ? csubf(cm1, dcm) : cm1);
   }
   return true;
+}
+
+template <int MODEL>
+__host__ __device__ __forceinline__ bool ap_terms_fast_t(const DevParams &P, cplx p, cplx aux, cplx aux2,
+                                                double a2, double w, int lay_mask, double eta_max,
+                                                cplx *eta_out, Coef *co /* [3], indexed by layer-1 */) {
+  const CoefRegSink sink{co};
+  return ap_terms_fast_s<MODEL>(P, p, aux, aux2, a2, w, lay_mask, eta_max, eta_out, sink);
 }
 
 __host__ __device__ __forceinline__ bool ap_terms_fast(const DevParams &P, cplx p, cplx aux, cplx aux2,

@@ -412,18 +412,30 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
           while (next_b - base <= cnt && next_b < NA) { seg += 1; next_b += G; }
           next_b -= (seg - seg0) * G;
 #endif
+#if UNC_REGMASK
+          const int hret = seg;
+          seg = hret & 0xff;
+#endif
           next_b += (seg - seg0) * G;
           jj = cnt;
           // fate of the intervals closed inside this chunk (see the comment at `dead`)
           if (lt_ok) {
             for (int sidx = max(seg0, 1); sidx < seg && !done; ++sidx) {
               int cur_bad = 0;
+#if UNC_REGMASK
+              if (((hret >> 8) & 3) == 1) {       // one interval closed: its fate came back in registers
+                cur_bad = (hret >> 12) & 0xff;
+                anyf |= (hret >> 20) & 0xff;
+              } else
+#endif
+              {
 #pragma unroll
-              for (int kq = 0; kq < ZL; ++kq) {
-                const cplx a = areas[kq][sidx];
-                const bool f = is_finite_fastc(a);
-                if (!f) cur_bad |= 1 << kq;
-                if (f && (a.re != 0.0 || a.im != 0.0)) anyf |= 1 << kq;
+                for (int kq = 0; kq < ZL; ++kq) {
+                  const cplx a = areas[kq][sidx];
+                  const bool f = is_finite_fastc(a);
+                  if (!f) cur_bad |= 1 << kq;
+                  if (f && (a.re != 0.0 || a.im != 0.0)) anyf |= 1 << kq;
+                }
               }
               dead |= cur_bad;
               if (__all_sync(0xffffffffu, (dead & anyf) == (1 << ZL) - 1)) {

@@ -1400,6 +1400,12 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
 #ifndef UNC_HOT_XB
 #define UNC_HOT_XB 1   // exception slot from pre-scaled other-layer coefficients (see eval8_scaled)
 #endif
+#ifndef UNC_REGMASK
+#define UNC_REGMASK 1     // hot8_chunk reports the fate of an interval it closes (packed into its return value)
+#endif
+#ifndef UNC_WYNN_LOZ2
+#define UNC_WYNN_LOZ2 0   // 1: Wynn-epsilon with two anti-diagonals in lockstep (wynn.cuh: wynn_loz2) -- measured slower
+#endif
 #ifndef UNC_SPX_POW
 #define UNC_SPX_POW 1  // exp(+-eta*D*kx) as a product of exp(+-eta*D*{1,2,4}) instead of a fourth exponential
 #endif
@@ -1568,11 +1574,28 @@ __device__ __noinline__ int hot8_chunk(const cplx *stage /* field 0 of the half-
                                        cplx *acc_io, cplx *areas, int seg, int seg_rel, int lim_rel, int G) {
   constexpr int AST = UNC_MAX_NACC + 1;
   cplx acc[8];
+#if UNC_REGMASK
+  int ncl = 0, bad = 0, nz = 0;
+#endif
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = acc_io[k];
   for (int j = 0; j < cnt; ++j) {
     eval8_scaled<KX, K0Z>(stage + j * ST8_JSTEP, L, Lx, z0, acc);
     if (j + 1 == seg_rel && seg_rel < lim_rel) {
+#if UNC_REGMASK
+      // fate of the interval just closed, from the registers: bit k of `bad` = not finite, of `nz` =
+      // finite and non-zero (the caller's early-stop bookkeeping; re-reading the areas from thread-
+      // local memory stalled on the load)
+      if (ncl == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const bool f = is_finite_fastc(acc[k]);
+          if (!f) bad |= 1 << k;
+          if (f && (acc[k].re != 0.0 || acc[k].im != 0.0)) nz |= 1 << k;
+        }
+      }
+      ncl += 1;
+#endif
 #pragma unroll
       for (int k = 0; k < 8; ++k) { areas[k * AST + seg] = acc[k]; acc[k] = mk(0.0, 0.0); }
       seg += 1;
@@ -1581,7 +1604,11 @@ __device__ __noinline__ int hot8_chunk(const cplx *stage /* field 0 of the half-
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc_io[k] = acc[k];
+#if UNC_REGMASK
+  return seg | (min(ncl, 3) << 8) | (bad << 12) | (nz << 20);
+#else
   return seg;
+#endif
 }
 
 
@@ -1589,61 +1616,71 @@ __device__ __noinline__ int hot8_chunk(const cplx *stage /* field 0 of the half-
 // kx (>= 0; other layer Lb) exp(+-eta*Dz*kx) -- as a product of the powers 1, 2, 4 of exp(+-eta*Dz)
 // (relative error a few ulp on top of kx times that of the factor, which is what the slot
 // recurrences carry anyway) -- times that layer's cp, cm.
+struct CoefStageSink {   // a layer's coefficients straight into the lane's stage entry
+  cplx *out;
+  __device__ __forceinline__ void set(int L, cplx k0, cplx cp, cplx cm) const {
+    out[(ST8_CO + 3 * L) * ST8_FSTEP] = k0;
+    out[(ST8_CO + 3 * L + 1) * ST8_FSTEP] = cp;
+    out[(ST8_CO + 3 * L + 2) * ST8_FSTEP] = cm;
+  }
+};
 template <int MODEL>
 __device__ __noinline__ int ap_terms_stage8_t(const DevParams &P, cplx p, cplx aux, cplx aux2, double a2,
                                               double w, int lay_mask, double eta_max, bool zuni,
                                               double Dz, int kx, int Lb, cplx *out /* field 0 of this lane's entry */) {
-  StageEnt8 e;
-  const bool ok = ap_terms_fast_t<MODEL>(P, p, aux, aux2, a2, w, lay_mask, eta_max, &e.eta, e.co);
-  e.sp = e.sm = e.spx = e.smx = mk(1.0, 0.0);
+  cplx eta;
+  const CoefStageSink sink{out};
+  const bool ok = ap_terms_fast_s<MODEL>(P, p, aux, aux2, a2, w, lay_mask, eta_max, &eta, sink);
+  out[ST8_ETA * ST8_FSTEP] = eta;
+  const cplx one = mk(1.0, 0.0);
+  cplx sp = one, sm = one, spx = one, smx = one;
 #if UNC_HOT_E2
-  e.sp2 = e.sm2 = mk(1.0, 0.0);
+  cplx sp2 = one, sm2 = one;
 #endif
   if (zuni && ok) {
-    const cbundle S = cexp_bundle(e.eta.re * Dz, e.eta.im * Dz);
-    e.sp = S.ep;
-    e.sm = S.em;
+    const cbundle S = cexp_bundle(eta.re * Dz, eta.im * Dz);
+    sp = S.ep;
+    sm = S.em;
 #if UNC_HOT_E2
-    e.sp2 = cmulf(S.ep, S.ep);
-    e.sm2 = cmulf(S.em, S.em);
+    sp2 = cmulf(S.ep, S.ep);
+    sm2 = cmulf(S.em, S.em);
 #endif
 #if UNC_SPX_POW && UNC_HOT_E2
     if (kx >= 1) {
-      cplx xp = mk(1.0, 0.0), xm = mk(1.0, 0.0);
-      if (kx & 1) { xp = S.ep; xm = S.em; }
+      if (kx & 1) { spx = S.ep; smx = S.em; }
       if (kx & 2) {
-        xp = (kx & 1) ? cmulf(xp, e.sp2) : e.sp2;
-        xm = (kx & 1) ? cmulf(xm, e.sm2) : e.sm2;
+        spx = (kx & 1) ? cmulf(spx, sp2) : sp2;
+        smx = (kx & 1) ? cmulf(smx, sm2) : sm2;
       }
       if (kx & 4) {
-        const cplx p4 = cmulf(e.sp2, e.sp2), m4 = cmulf(e.sm2, e.sm2);
-        xp = (kx & 3) ? cmulf(xp, p4) : p4;
-        xm = (kx & 3) ? cmulf(xm, m4) : m4;
+        const cplx p4 = cmulf(sp2, sp2), m4 = cmulf(sm2, sm2);
+        spx = (kx & 3) ? cmulf(spx, p4) : p4;
+        smx = (kx & 3) ? cmulf(smx, m4) : m4;
       }
-      e.spx = xp;
-      e.smx = xm;
     }
 #else
     if (kx >= 1) {
       const double Dx = Dz * (double)kx;
-      const cbundle X = cexp_bundle(e.eta.re * Dx, e.eta.im * Dx);
-      e.spx = X.ep;
-      e.smx = X.em;
+      const cbundle X = cexp_bundle(eta.re * Dx, eta.im * Dx);
+      spx = X.ep;
+      smx = X.em;
+    }
+#endif
+#if UNC_HOT_XB
+    if (kx >= 0) {
+      // the other layer's cp, cm read back from the stage (no dynamic indexing of registers)
+      spx = cmulf(out[(ST8_CO + 3 * Lb + 1) * ST8_FSTEP], spx);
+      smx = cmulf(out[(ST8_CO + 3 * Lb + 2) * ST8_FSTEP], smx);
     }
 #endif
   }
-  {
-    const cplx *src = (const cplx *)&e;
-#pragma unroll
-    for (int f = 0; f < ST8_NF; ++f) out[f * ST8_FSTEP] = src[f];
-  }
-#if UNC_HOT_XB
-  if (zuni && ok && kx >= 0) {
-    // this layer's cp, cm read back from the stage: no dynamic indexing of the local copy
-    const cplx bcp = out[(ST8_CO + 3 * Lb + 1) * ST8_FSTEP], bcm = out[(ST8_CO + 3 * Lb + 2) * ST8_FSTEP];
-    out[ST8_SPX * ST8_FSTEP] = cmulf(bcp, e.spx);
-    out[ST8_SMX * ST8_FSTEP] = cmulf(bcm, e.smx);
-  }
+  out[ST8_SP * ST8_FSTEP] = sp;
+  out[ST8_SM * ST8_FSTEP] = sm;
+  out[ST8_SPX * ST8_FSTEP] = spx;
+  out[ST8_SMX * ST8_FSTEP] = smx;
+#if UNC_HOT_E2
+  out[ST8_SP2 * ST8_FSTEP] = sp2;
+  out[ST8_SM2 * ST8_FSTEP] = sm2;
 #endif
   return ok ? 1 : 0;
 }
@@ -1730,7 +1767,11 @@ __device__ __noinline__ int finish8(cplx *areas, int nacc, cplx lt, cplx *out, c
       infint = ar[1];
 #else
       // wscr: this lane's column of the warp's (now idle) stage, [table column][32 lanes]
+#if UNC_WYNN_LOZ2
+      if (wscr && nacc <= 14) infint = wynn_loz2(ar + 1, nacc, wscr, 32);
+#else
       if (wscr && nacc <= 14) infint = wynn_loz(ar + 1, nacc, wscr, 32);
+#endif
       else infint = wynn_grid(ar + 1, nacc);
 #endif
     } else stale |= 1 << k;

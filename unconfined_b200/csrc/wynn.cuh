@@ -146,6 +146,97 @@ __host__ __device__ __forceinline__ cplx wynn_loz(const cplx *series, int nacc, 
   return D[(ns - 2) * stride];
 }
 
+// wynn_loz with TWO anti-diagonals in flight.  A diagonal is one dependent chain (difference,
+// |.|^2, reciprocal with two Newton steps, FMA: ~10 FP64 instructions deep per entry, 66 entries
+// for 12 terms), during which the FP64 pipe idles two thirds of the time.  Entry j of diagonal
+// n+1 needs entry j of diagonal n (what wynn_loz parks in D[j]) and its own entry j-1, so the
+// diagonals n ("A") and n+1 ("B") run in lockstep, B one column behind A and fed from A through a
+// register: iteration i does A's column i and B's column i-1, two independent chains.  A never
+// writes D (B overwrites every column it would have written; columns B does not reach are dead,
+// see below).  The arithmetic of every entry is that of wynn_loz, bit for bit.
+// Exit semantics: a step (diagonal, column j) is executed iff j < jlim at that moment; within an
+// iteration A's step is settled before B's.  B is always behind A, so this admits exactly the
+// steps of the sequential order (all of A, then all of B) whose cancels can still win: the
+// reference returns the cancel with the smallest column, earliest row first.
+__host__ __device__ __forceinline__ cplx wynn_loz2(const cplx *series, int nacc, cplx *D, int stride) {
+  int ns = nacc;
+  for (int i = 0; i < nacc; ++i)
+    if (!is_finite_fastc(series[i])) { ns = i; break; }
+  if (ns < nacc && ns < 4) return mk(-999999.875, 0.0);  // real(4) literal -999999.9
+  const double eps2 = 2.220446049250313e-16 * 2.220446049250313e-16;
+  cplx run = mk(0.0, 0.0), best = mk(0.0, 0.0), keep_odd = mk(0.0, 0.0);
+  int jlim = 1 << 30;  // no cancel seen yet
+  // diagonals n0..ns go in pairs (so that the last one, which captures eps(2, ns-3), is a "B")
+  const int n0 = ((ns - 1) & 1) ? 3 : 2;
+  for (int n = 1; n < n0 && n <= ns; ++n) {   // diagonal 1 (and 2): as wynn_loz
+    const cplx term = series[n - 1];
+    run = mk(run.re + term.re, run.im + term.im);
+    cplx cur = run;
+    if (n == 2) {
+      const cplx a = D[0];
+      if (n == ns && 0 == ns - 3) keep_odd = a;
+      D[0] = cur;
+      const double dr = cur.re - a.re, di = cur.im - a.im;
+      const double n2 = fma(dr, dr, di * di);
+      if (n2 > eps2) {
+        const double inv = rcp_fast(n2);
+        cur = mk(fma(dr, inv, 0.0), fma(-di, inv, 0.0));   // eps(:,-1) = 0
+      } else {
+        best = cur;
+        jlim = 0;
+      }
+    }
+    if (n - 1 < jlim) D[(n - 1) * stride] = cur;
+  }
+  for (int n = n0; n + 1 <= ns; n += 2) {
+    const cplx tA = series[n - 1], tB = series[n];
+    const cplx runA = mk(run.re + tA.re, run.im + tA.im);
+    run = mk(runA.re + tB.re, runA.im + tB.im);
+    cplx curA = runA, pm1A = mk(0.0, 0.0), curB = run, pm1B = mk(0.0, 0.0);
+    cplx sav = mk(0.0, 0.0);        // A's value at column i-1 = what wynn_loz would have left in D[i-1]
+    bool liveA = true, liveB = true;
+    const bool lastB = (n + 1 == ns);
+    for (int i = 0; i <= n; ++i) {
+      const cplx cA = curA;
+      const bool doA = liveA && i <= n - 2 && i < jlim;
+      // both chains' arithmetic first (independent), the bookkeeping after
+      const cplx aA = doA ? D[i * stride] : mk(0.0, 0.0);
+      const double drA = cA.re - aA.re, diA = cA.im - aA.im;
+      const double n2A = fma(drA, drA, diA * diA);
+      const double invA = rcp_fast(n2A);
+      const cplx newA = mk(fma(drA, invA, pm1A.re), fma(-diA, invA, pm1A.im));
+      const cplx aB = sav;
+      const double drB = curB.re - aB.re, diB = curB.im - aB.im;
+      const double n2B = fma(drB, drB, diB * diB);
+      const double invB = rcp_fast(n2B);
+      const cplx newB = mk(fma(drB, invB, pm1B.re), fma(-diB, invB, pm1B.im));
+      // selects only (no branches): both chains stay in one basic block and ptxas interleaves them
+      const bool okA = doA && (n2A > eps2), cxA = doA && !(n2A > eps2);
+      curA = okA ? newA : curA;
+      pm1A = okA ? aA : pm1A;
+      best = cxA ? cA : best;
+      jlim = cxA ? i : jlim;
+      liveA = okA;
+      const int j = i - 1;
+      const bool doB = liveB && j >= 0 && j < jlim;      // j <= n-1 = (n+1)-2 by the loop bound
+      const bool okB = doB && (n2B > eps2), cxB = doB && !(n2B > eps2);
+      keep_odd = (doB && lastB && j == ns - 3) ? aB : keep_odd;
+      if (doB) D[j * stride] = curB;
+      best = cxB ? curB : best;
+      jlim = cxB ? j : jlim;
+      curB = okB ? newB : curB;
+      pm1B = okB ? aB : pm1B;
+      liveB = okB || (j < 0);
+      sav = cA;
+      if (!liveA && !liveB) break;
+    }
+    if (n < jlim) D[n * stride] = curB;
+  }
+  if (jlim < (1 << 30)) return best;
+  if (ns & 1) return keep_odd;
+  return D[(ns - 2) * stride];
+}
+
 // The same algorithm with the epsilon table held in REGISTERS (north_star): anti-diagonal
 // ("moving lozenge") order needs only one entry per column, D[j] = eps(n-j, j) of the last
 // completed anti-diagonal n, instead of two full columns in local memory (which misses L1
