@@ -126,7 +126,7 @@ def test_scattered_points_c5b_sample():
     check_parity(sg, dg, so, do, sps, spd, what="scatter")
 
 
-@pytest.mark.parametrize("nz", [1, 2, 3, 5, 12, 33, 40, 70])   # 70: the 128-z kernel with padding slots
+@pytest.mark.parametrize("nz", [1, 2, 3, 5, 12, 33, 40, 63, 70])   # from 33: the 128-z kernel with padding slots
 def test_ragged_z_counts_and_kernel_agreement(nz):
     d, pd = load_deck("cape-cod-neuman74.in")
     zD = np.linspace(0.0, 1.0, nz) if nz > 1 else np.array([0.4])

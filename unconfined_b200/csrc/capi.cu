@@ -334,10 +334,12 @@ DevCtx g_ctx[16];
 std::atomic<int> g_carry{1};   // unc_set_carry
 std::atomic<int> g_force{0};   // unc_debug_force_kernel: 0 auto, 1 point, 2 grid, 3 grid (lanes<->z kernel only), 4 grid (128-z kernel from nz = 32)
 // columns of at least this many z go to the 128-z persistent kernel (its padding slots idle):
-// measured on 1024 r x nz x 2 t of C5a, lanes<->z kernel vs 128-z kernel: nz=48 31.7 vs 56.4 ms,
-// nz=64 32.7 vs 22.1, nz=80 60.5 vs 22.4, nz=96 61.7 vs 23.0 (profiles/r02_nz_crossover.txt)
+// measured on 1024 r x nz x 2 t of C5a, lanes<->z kernel vs 128-z kernel: nz=32 17.2 vs 19.2 ms,
+// nz=40 30.9 vs 19.9, nz=48 31.3 vs 19.8, nz=64 32.4 vs 19.7, nz=96 60.1 vs 20.5
+// (profiles/r02_nz_crossover.txt; before the padding slots were taken out of the early-stop
+// condition the 128-z kernel needed 54 ms below nz = 64 and the crossover was 64)
 #ifndef UNC_GRID8_MIN_NZ
-#define UNC_GRID8_MIN_NZ 64
+#define UNC_GRID8_MIN_NZ 33
 #endif
 
 // the library switches devices internally; the caller's current device is restored on return
@@ -503,7 +505,7 @@ int launch(int dev, StreamRes &r, const unc::DevParams &P, const unc::Job &J, cu
   bool grid = J.nz >= 12;
   // a small contour grid (fewer column CTAs than SMs) is a latency problem: the point kernel
   // spreads it over nz/4 times as many CTAs (hantush-contours deck, 30 r x 20 z: 6.9 ms -> <1 ms)
-  if (grid && J.nz < UNC_GRID8_MIN_NZ && J.ncol * ((J.nz + 31) / 32) < (long long)g_ctx[dev].sm_count) grid = false;
+  if (grid && J.nz < 64 && J.ncol * ((J.nz + 31) / 32) < (long long)g_ctx[dev].sm_count) grid = false;
   if (force == 1) grid = false;
   if (force == 2 || force == 3 || force == 4) grid = true;
   if (grid) return launch_grid(dev, r, P, J, st);

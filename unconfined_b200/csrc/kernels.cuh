@@ -1128,6 +1128,12 @@ struct StageEnt {
   cplx eta;
   Coef co[3];
 };
+struct CoefAosSink {   // ap_terms_fast_s sink: a layer's coefficients into a staged entry in shared memory
+  Coef *co;
+  __device__ __forceinline__ void set(int L, cplx k0, cplx cp, cplx cm) const {
+    co[L].k0 = k0; co[L].cp = cp; co[L].cm = cm;
+  }
+};
 
 __host__ __device__ inline size_t grid_smem_bytes(int np, int na_seq, int ZL) {
   size_t b = 0;
@@ -1273,9 +1279,11 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
       {
         const int idx = base + lane;
         if (idx < NA) {
-          StageEnt e;
-          ok = ap_terms_fast(P, pp, aux, aux2, s_a2[idx], s_wj[idx], lay_mask, eta_max, &e.eta, e.co) ? 1 : 0;
-          stage[lane] = e;
+          // each layer's coefficients straight into the stage entry (no 20-double entry in registers)
+          const CoefAosSink sink{stage[lane].co};
+          cplx eta;
+          ok = ap_terms_fast_s<-1>(P, pp, aux, aux2, s_a2[idx], s_wj[idx], lay_mask, eta_max, &eta, sink) ? 1 : 0;
+          stage[lane].eta = eta;
         }
         okv[lane] = ok;
       }
