@@ -170,13 +170,20 @@ def cpu_build():
     return {"flags": flags, "fortran_compiler": fc[0] if fc else None}
 
 
-def sass_sha256():
-    """Hash of the SASS of the library being timed (identifies the build an ncu capture was taken from)."""
+def sass_sha256(so=None):
+    """Hash of the SASS of the library being timed (identifies the build an ncu capture was taken from).
+    The dump's `identifier = <source path as passed to nvcc>` lines are left out: the same sources
+    built under another directory are the same build."""
     import hashlib
-    import unconfined_b200.api as api
+    if so is None:
+        import unconfined_b200.api as api
+        so = api._SO
     try:
-        out = subprocess.run(["cuobjdump", "-sass", api._SO], capture_output=True, timeout=120).stdout
-        return hashlib.sha256(out).hexdigest() if out else None
+        out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, timeout=120).stdout
+        if not out:
+            return None
+        keep = [ln for ln in out.split(b"\n") if not ln.lstrip().startswith(b"identifier =")]
+        return hashlib.sha256(b"\n".join(keep)).hexdigest()
     except Exception:  # noqa: BLE001
         return None
 

@@ -19,6 +19,6 @@ parity) timeout 1500 python tools/parity_report.py --out gpurun_out/${T}_parity.
 decks)  timeout 600 python tools/bench_decks.py > gpurun_out/${T}_decks.txt 2>&1; cat gpurun_out/${T}_decks.txt ;;
 launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/${T}_ncu_launch.log 2>&1; tail -2 gpurun_out/${T}_ncu_launch.log ;;
 ncu_point) timeout 900 ncu --set full --clock-control none --import-source on -k regex:lh_point --launch-skip 1 -c 1 -o gpurun_out/${T}_point -f python tools/bench_c5b.py 15 1 > gpurun_out/${T}_ncu_point.log 2>&1; tail -2 gpurun_out/${T}_ncu_point.log ;;
-ncu_grid) cuobjdump -sass unconfined_b200/libunconfined_b200.so | sha256sum > gpurun_out/${T}_sass.sha; timeout 900 ncu --set full --clock-control none --import-source on -k regex:lh_grid8 --launch-skip 1 -c 1 -o gpurun_out/${T}_grid -f python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/${T}_ncu_grid.log 2>&1; tail -2 gpurun_out/${T}_ncu_grid.log ;;
+ncu_grid) python -c "import bench; print(bench.sass_sha256('unconfined_b200/libunconfined_b200.so'))" > gpurun_out/${T}_sass.sha; timeout 900 ncu --set full --clock-control none --import-source on -k regex:lh_grid8 --launch-skip 1 -c 1 -o gpurun_out/${T}_grid -f python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/${T}_ncu_grid.log 2>&1; tail -2 gpurun_out/${T}_ncu_grid.log ;;
 esac
 done
