@@ -334,7 +334,6 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
       Lx = myL[0];
 #pragma unroll
       for (int kq = 1; kq < ZL; ++kq) if (kq == kx) Lx = myL[kq];
-#if UNC_HOT_XB
       // ... whose lanes off the common layer all lie on ONE other layer Lb (padding lanes, whose
       // results are dropped, join the common layer)
       Lb = Lc;
@@ -344,7 +343,6 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
         if (offl) Lb = __shfl_sync(0xffffffffu, Lx, __ffs(offl) - 1);
         if (!__all_sync(0xffffffffu, Lx == Lc || Lx == Lb)) hot_ok = false;
       }
-#endif
       // k0 of the common layer is exactly zero below/above the screen of the Hantush-type models
       k0z = (P.model == 1 || P.model == 2 || P.model == 3 || P.model == 5) && Lc != 1;
     }
@@ -418,22 +416,18 @@ lh_grid8_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job
           while (next_b - base <= cnt && next_b < NA) { seg += 1; next_b += G; }
           next_b -= (seg - seg0) * G;
 #endif
-#if UNC_REGMASK
           const int hret = seg;
           seg = hret & 0xff;
-#endif
           next_b += (seg - seg0) * G;
           jj = cnt;
           // fate of the intervals closed inside this chunk (see the comment at `dead`)
           if (lt_ok) {
             for (int sidx = max(seg0, 1); sidx < seg && !done; ++sidx) {
               int cur_bad = 0;
-#if UNC_REGMASK
               if (((hret >> 8) & 3) == 1) {       // one interval closed: its fate came back in registers
                 cur_bad = (hret >> 12) & 0xff;
                 anyf |= (hret >> 20) & 0xff;
               } else
-#endif
               {
 #pragma unroll
                 for (int kq = 0; kq < ZL; ++kq) {

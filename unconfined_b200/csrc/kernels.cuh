@@ -1402,34 +1402,15 @@ lh_grid_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Job 
 
 // ---------------------------------------------------------------------------
 // Eight z-slots per lane, two Laplace parameters per warp (lh_grid8_kernel below).
-#ifndef UNC_HOT_E2
-#define UNC_HOT_E2 1   // slot values from two-step anchors (see eval8_scaled); 0 = one-step recurrences
-#endif
-#ifndef UNC_HOT_XB
-#define UNC_HOT_XB 1   // exception slot from pre-scaled other-layer coefficients (see eval8_scaled)
-#endif
-#ifndef UNC_REGMASK
-#define UNC_REGMASK 1     // hot8_chunk reports the fate of an interval it closes (packed into its return value)
-#endif
 #ifndef UNC_WYNN_LOZ2
 #define UNC_WYNN_LOZ2 0   // 1: Wynn-epsilon with two anti-diagonals in lockstep (wynn.cuh: wynn_loz2) -- measured slower
-#endif
-#ifndef UNC_SPX_POW
-#define UNC_SPX_POW 1  // exp(+-eta*D*kx) as a product of exp(+-eta*D*{1,2,4}) instead of a fourth exponential
-#endif
-#if UNC_HOT_XB && !UNC_HOT_E2
-#error "UNC_HOT_XB needs UNC_HOT_E2"
 #endif
 struct StageEnt8 {   // register-side image of one staged abscissa; see st8_idx for the shared-memory layout
   cplx eta;
   Coef co[3];
   cplx sp, sm;    // exp(+-eta*D), D = z spacing between a lane's slots (16 grid steps)
-  // UNC_HOT_XB: cp, cm of the exception slot's OTHER layer times exp(+-eta*D*kx);
-  // otherwise exp(+-eta*D*kx) itself: straight from slot 0 to the one slot with lane-dependent layers
-  cplx spx, smx;
-#if UNC_HOT_E2
+  cplx spx, smx;  // cp, cm of the exception slot's OTHER layer times exp(+-eta*D*kx)
   cplx sp2, sm2;  // exp(+-2*eta*D)
-#endif
 };
 // A warp's stage in shared memory: 32 entries (16 abscissae x the warp's two Laplace parameters) of
 // ST8_NF complex fields, FIELD-MAJOR: field f of abscissa j of half-warp h at complex index
@@ -1437,27 +1418,15 @@ struct StageEnt8 {   // register-side image of one staged abscissa; see st8_idx 
 // field, and the two half-warps of the consumer read one 32-byte segment -- with entry-major
 // 256-byte entries every lane of a store hit the same banks (measured: 95.3 instead of 90.5
 // ms/step on C5a in spite of 13 % fewer FP64 instructions in the hot loop).
-#ifndef UNC_STAGE_SOA
-#define UNC_STAGE_SOA 1
-#endif
 constexpr int ST8_NF = (int)(sizeof(StageEnt8) / sizeof(cplx));
-static_assert(ST8_NF == (UNC_HOT_E2 ? 16 : 14) && sizeof(Coef) == 3 * sizeof(cplx), "stage field numbering");
+static_assert(ST8_NF == 16 && sizeof(Coef) == 3 * sizeof(cplx), "stage field numbering");
 enum { ST8_ETA = 0, ST8_CO = 1, ST8_SP = 10, ST8_SM = 11, ST8_SPX = 12, ST8_SMX = 13, ST8_SP2 = 14, ST8_SM2 = 15 };
 __host__ __device__ __forceinline__ int st8_idx(int f, int j, int h) {
-#if UNC_STAGE_SOA
   return f * 32 + 2 * j + h;
-#else
-  return (h * 16 + j) * ST8_NF + f;
-#endif
 }
 // complex-index step from abscissa j to j+1 and from field f to f+1
-#if UNC_STAGE_SOA
 #define ST8_JSTEP 2
 #define ST8_FSTEP 32
-#else
-#define ST8_JSTEP ST8_NF
-#define ST8_FSTEP 1
-#endif
 
 // One abscissa for the eight slots of a lane.  The slot values of the common-layer slots are
 // advanced ALREADY SCALED by the coefficients, P_k = cp e^{eta z_k}, M_k = cm e^{-eta z_k}.
@@ -1465,14 +1434,14 @@ __host__ __device__ __forceinline__ int st8_idx(int f, int j, int h) {
 // in its own direction); an odd slot is its anchor times exp(+-eta D), fused into the
 // accumulation: acc += P*E is four FMA, where advancing P and adding it are four multiply/FMA
 // plus two adds -- 36 instead of 44 FP64 instructions per direction for eight slots, and
-// dependent chains of three instead of seven multiplies.  (UNC_HOT_E2 = 0: every slot advanced
-// from its neighbour.)
+// dependent chains of three instead of seven multiplies (every slot advanced from its neighbour
+// before: profiles/r02_grid_kernel_variants.txt).
 // Slot KX (if >= 0) has lane-dependent layers.  Lanes on the common layer (Lx == L) treat it like
 // any other slot.  The other lanes all lie on ONE other layer (the caller checks that); the stage
 // holds that layer's cp, cm already multiplied by exp(+-eta D KX), so their value is
 // k0' + spx*E0 + smx*E0' from the unscaled start exponentials.  Both kinds run the same eight
-// FMA on lane-selected operands.  (UNC_HOT_XB = 0: exponentials of slot KX from slot 0 in one
-// step, then the per-lane layer's coefficients: eight instructions more.)
+// FMA on lane-selected operands (before: exponentials of slot KX from slot 0 in one step, then
+// the per-lane layer's coefficients -- eight instructions more).
 // K0Z: k0 of the common layer is exactly zero.
 template <int KX, bool K0Z>
 __device__ __forceinline__ void eval8_scaled(const cplx *e, int L, int Lx, double z0, cplx *acc) {
@@ -1487,28 +1456,9 @@ __device__ __forceinline__ void eval8_scaled(const cplx *e, int L, int Lx, doubl
   exp_pm_core(eta.re * z0, &ep, &em, &cc, &ss, &kk);
   sincos_q(eta.im * z0, &s, &cs);
   const cplx Ep = mk(ep * cs, ep * s), Em = mk(em * cs, -(em * s));
-#if !UNC_HOT_XB
-  if (KX >= 0) {
-    Coef cx;
-    cx.k0 = ST8F(ST8_CO + 3 * Lx); cx.cp = ST8F(ST8_CO + 3 * Lx + 1); cx.cm = ST8F(ST8_CO + 3 * Lx + 2);
-    const cplx Ex = (KX == 0) ? Ep : cmulf(Ep, ST8F(ST8_SPX)), Mx = (KX == 0) ? Em : cmulf(Em, ST8F(ST8_SMX));
-    double fr = fma(cx.cp.re, Ex.re, cx.k0.re);
-    fr = fma(-cx.cp.im, Ex.im, fr);
-    fr = fma(cx.cm.re, Mx.re, fr);
-    fr = fma(-cx.cm.im, Mx.im, fr);
-    double fi = fma(cx.cp.re, Ex.im, cx.k0.im);
-    fi = fma(cx.cp.im, Ex.re, fi);
-    fi = fma(cx.cm.re, Mx.im, fi);
-    fi = fma(cx.cm.im, Mx.re, fi);
-    acc[KX < 0 ? 0 : KX] = mk(acc[KX < 0 ? 0 : KX].re + fr, acc[KX < 0 ? 0 : KX].im + fi);
-  }
-#endif
   cplx Pk = cmulf(c.cp, Ep), Mk = cmulf(c.cm, Em);
-#if UNC_HOT_E2
   const cplx e1p = ST8F(ST8_SP), e1m = ST8F(ST8_SM), e2p = ST8F(ST8_SP2), e2m = ST8F(ST8_SM2);
-#if UNC_HOT_XB
   const bool isB = (KX >= 0) && Lx != L;
-#endif
 #pragma unroll
   for (int k = 0; k < 8; k += 2) {
 #pragma unroll
@@ -1533,7 +1483,6 @@ __device__ __forceinline__ void eval8_scaled(const cplx *e, int L, int Lx, doubl
           acc[q] = mk(fr, fi);
         }
       }
-#if UNC_HOT_XB
       else {
         // common-layer lanes: anchor (times exp(+-eta D) at an odd slot); the others: start
         // exponentials times the pre-scaled coefficients of their layer
@@ -1552,21 +1501,9 @@ __device__ __forceinline__ void eval8_scaled(const cplx *e, int L, int Lx, doubl
         fi = fma(X2.im, Y2.re, fi);
         acc[q] = mk(fr, fi);
       }
-#endif
     }
     if (k < 6) { Pk = cmulf(Pk, e2p); Mk = cmulf(Mk, e2m); }
   }
-#else
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    if (k != KX) {
-      double fr = Pk.re + Mk.re, fi = Pk.im + Mk.im;
-      if (!K0Z) { fr += c.k0.re; fi += c.k0.im; }
-      acc[k] = mk(acc[k].re + fr, acc[k].im + fi);
-    }
-    if (k < 7 && !(KX == 7 && k == 6)) { Pk = cmulf(Pk, ST8F(ST8_SP)); Mk = cmulf(Mk, ST8F(ST8_SM)); }
-  }
-#endif
 #undef ST8F
 }
 
@@ -1582,15 +1519,12 @@ __device__ __noinline__ int hot8_chunk(const cplx *stage /* field 0 of the half-
                                        cplx *acc_io, cplx *areas, int seg, int seg_rel, int lim_rel, int G) {
   constexpr int AST = UNC_MAX_NACC + 1;
   cplx acc[8];
-#if UNC_REGMASK
   int ncl = 0, bad = 0, nz = 0;
-#endif
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = acc_io[k];
   for (int j = 0; j < cnt; ++j) {
     eval8_scaled<KX, K0Z>(stage + j * ST8_JSTEP, L, Lx, z0, acc);
     if (j + 1 == seg_rel && seg_rel < lim_rel) {
-#if UNC_REGMASK
       // fate of the interval just closed, from the registers: bit k of `bad` = not finite, of `nz` =
       // finite and non-zero (the caller's early-stop bookkeeping; re-reading the areas from thread-
       // local memory stalled on the load)
@@ -1603,7 +1537,6 @@ __device__ __noinline__ int hot8_chunk(const cplx *stage /* field 0 of the half-
         }
       }
       ncl += 1;
-#endif
 #pragma unroll
       for (int k = 0; k < 8; ++k) { areas[k * AST + seg] = acc[k]; acc[k] = mk(0.0, 0.0); }
       seg += 1;
@@ -1612,11 +1545,7 @@ __device__ __noinline__ int hot8_chunk(const cplx *stage /* field 0 of the half-
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc_io[k] = acc[k];
-#if UNC_REGMASK
   return seg | (min(ncl, 3) << 8) | (bad << 12) | (nz << 20);
-#else
-  return seg;
-#endif
 }
 
 
@@ -1642,18 +1571,13 @@ __device__ __noinline__ int ap_terms_stage8_t(const DevParams &P, cplx p, cplx a
   out[ST8_ETA * ST8_FSTEP] = eta;
   const cplx one = mk(1.0, 0.0);
   cplx sp = one, sm = one, spx = one, smx = one;
-#if UNC_HOT_E2
   cplx sp2 = one, sm2 = one;
-#endif
   if (zuni && ok) {
     const cbundle S = cexp_bundle(eta.re * Dz, eta.im * Dz);
     sp = S.ep;
     sm = S.em;
-#if UNC_HOT_E2
     sp2 = cmulf(S.ep, S.ep);
     sm2 = cmulf(S.em, S.em);
-#endif
-#if UNC_SPX_POW && UNC_HOT_E2
     if (kx >= 1) {
       if (kx & 1) { spx = S.ep; smx = S.em; }
       if (kx & 2) {
@@ -1666,30 +1590,18 @@ __device__ __noinline__ int ap_terms_stage8_t(const DevParams &P, cplx p, cplx a
         smx = (kx & 3) ? cmulf(smx, m4) : m4;
       }
     }
-#else
-    if (kx >= 1) {
-      const double Dx = Dz * (double)kx;
-      const cbundle X = cexp_bundle(eta.re * Dx, eta.im * Dx);
-      spx = X.ep;
-      smx = X.em;
-    }
-#endif
-#if UNC_HOT_XB
     if (kx >= 0) {
       // the other layer's cp, cm read back from the stage (no dynamic indexing of registers)
       spx = cmulf(out[(ST8_CO + 3 * Lb + 1) * ST8_FSTEP], spx);
       smx = cmulf(out[(ST8_CO + 3 * Lb + 2) * ST8_FSTEP], smx);
     }
-#endif
   }
   out[ST8_SP * ST8_FSTEP] = sp;
   out[ST8_SM * ST8_FSTEP] = sm;
   out[ST8_SPX * ST8_FSTEP] = spx;
   out[ST8_SMX * ST8_FSTEP] = smx;
-#if UNC_HOT_E2
   out[ST8_SP2 * ST8_FSTEP] = sp2;
   out[ST8_SM2 * ST8_FSTEP] = sm2;
-#endif
   return ok ? 1 : 0;
 }
 
