@@ -155,7 +155,7 @@ int unc_release_stream(void *stream);     /* frees what the *_device entry point
 int unc_set_carry(int32_t on);            /* default 1: see UNC_FLAG_STALE_INFINT */
 int unc_debug_cbesk01(int32_t n, const double *z /* [2n] */, double *out /* [4n]: K0, K1 */); /* test hook: device cbknu */
 int unc_debug_force_kernel(int32_t which);/* test hook: 0 auto, 1 point kernel, 2 grid kernels,
-                                             3 lanes<->z grid kernel even for nz >= 64,
+                                             3 lanes<->z grid kernel even for nz >= 33,
                                              4 128-z persistent kernel from nz = 32 */
 const char *unc_last_error(void);         /* thread-local message for the last failure */
 const char *unc_version(void);

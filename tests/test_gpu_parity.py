@@ -207,7 +207,7 @@ GRID_DECKS = ["theis-input.dat", "hantush-input.dat", "hantush-storage-input.dat
 
 @pytest.mark.parametrize("name", GRID_DECKS)
 def test_every_model_through_the_128z_grid_kernels(name):
-    """Models 0-6 through lh_grid8_kernel (nz >= 64): z-lists that stay in one layer, straddle
+    """Models 0-6 through lh_grid8_kernel (nz >= 33): z-lists that stay in one layer, straddle
     one layer boundary in one slot, and cross both boundaries; checked against the lanes<->z
     grid kernel and the point kernel (themselves held to the oracle on the decks above) and,
     on a sample, against the oracle with its noise envelope."""

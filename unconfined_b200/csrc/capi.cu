@@ -984,7 +984,7 @@ int unc_debug_cbesk01(int32_t n, const double *z, double *out) {
 }
 
 /* test hook: pin the kernel family (0 auto, 1 point kernel, 2 grid kernels, 3 the lanes<->z
- * grid kernel even for nz >= 64; 4 the 128-z kernel from nz = 32); never needed by a caller of the product */
+ * grid kernel even for nz >= 33; 4 the 128-z kernel from nz = 32); never needed by a caller of the product */
 int unc_debug_force_kernel(int32_t which) {
   if (which < 0 || which > 4) return fail(UNC_ERR_BAD_ARG, "which must be 0..4");
   g_force.store(which);

@@ -1,4 +1,4 @@
-// lh_grid8_kernel: the persistent kernel for contour grids (nz >= 64), the benchmarked kernel.
+// lh_grid8_kernel: the persistent kernel for contour grids (nz >= 33), the benchmarked kernel.
 // Included at the end of kernels.cuh (it uses item_tables, ap_terms_stage8, hot8_chunk, slow8_run,
 // finish8 and dehoog_lane from there).
 #pragma once
@@ -138,7 +138,7 @@ __device__ __noinline__ void grid8_tjob(const DevParams &P, const Job &J, int kn
 }
 
 // ---------------------------------------------------------------------------
-// Grid kernel for contour grids (nz >= 64): persistent CTAs (one 16-warp CTA per SM) draw work
+// Grid kernel for contour grids (nz >= 33): persistent CTAs (one 16-warp CTA per SM) draw work
 // items (one (t,r) column x up to 128 z) from a global atomic counter, so the few expensive
 // columns (literal path at small rD) do not leave SMs idle.  Lanes <-> z with EIGHT z-slots per
 // lane and TWO Laplace parameters per warp (lanes 0-15 <-> p = 2*job, lanes 16-31 <-> p =
